@@ -1,0 +1,110 @@
+// Error plumbing, device queries and TMA tensor-map encoding for libspegnet_b200.so.
+#include "common.h"
+
+#include <atomic>
+#include <cstring>
+#include <mutex>
+
+namespace spg {
+
+std::atomic<long long> g_launches{0};
+
+char* error_buffer() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+// libcuda is not linked (the .so must load on a GPU-less build box); the encoder is looked up lazily.
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims,
+           const cuuint64_t* strides, const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    if (fn == nullptr) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(SPG_ERR_INVALID, "TMA operand must be 16-byte aligned");
+    cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box,
+                    elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SPG_OK;
+}
+
+}  // namespace
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_pitch_bytes,
+                 uint32_t box_rows) {
+    if (row_pitch_bytes % 16 != 0) return fail(SPG_ERR_INVALID, "row pitch %llu B is not a multiple of 16", (unsigned long long)row_pitch_bytes);
+    if (box_rows == 0 || box_rows > 256) return fail(SPG_ERR_INVALID, "TMA box rows %u out of range", box_rows);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_pitch_bytes};
+    cuuint32_t box[2] = {64, box_rows};
+    return encode(out, base, 2, dims, strides, box);
+}
+
+int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                   uint32_t box_h, uint32_t box_w) {
+    if ((C * 2) % 16 != 0) return fail(SPG_ERR_INVALID, "channel pitch must be a multiple of 16 bytes");
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {64, box_w, box_h, 1};
+    return encode(out, base, 4, dims, strides, box);
+}
+
+}  // namespace spg
+
+extern "C" int spg_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" const char* spg_last_error(void) { return spg::error_buffer(); }
+
+extern "C" int spg_device_check(void) {
+    int dev = 0;
+    SPG_CHECK_CUDA(cudaGetDevice(&dev));
+    int major = 0, minor = 0;
+    SPG_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    SPG_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    if (major != 10) return spg::fail(SPG_ERR_UNSUPPORTED, "device is sm_%d%d; this library is sm_100a only", major, minor);
+    return SPG_OK;
+}
+
+extern "C" long long spg_launch_count(void) { return spg::g_launches.load(std::memory_order_relaxed); }
+extern "C" void spg_launch_count_reset(void) { spg::g_launches.store(0, std::memory_order_relaxed); }

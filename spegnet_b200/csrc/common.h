@@ -1,0 +1,45 @@
+// Host-side helpers shared by every translation unit of libspegnet_b200.so:
+// error reporting behind the C-ABI (include/spegnet_b200.h) and TMA tensor-map encoding.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/spegnet_b200.h"
+
+namespace spg {
+
+// Thread-local last-error text returned by spg_last_error().
+char* error_buffer();
+int fail(int code, const char* fmt, ...);
+
+#define SPG_CHECK_ARG(cond, ...)                                  \
+    do {                                                          \
+        if (!(cond)) return ::spg::fail(SPG_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+#define SPG_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::spg::fail(SPG_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                  \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                   \
+    } while (0)
+
+// Launch-error check that never synchronises (the C-ABI contract: no sync inside).
+#define SPG_CHECK_LAUNCH() SPG_CHECK_CUDA(cudaPeekAtLastError())
+
+// bf16 K-major 2-D operand [rows, cols] (cols contiguous), box = [box_rows, 64 cols], 128B swizzle.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+                 uint64_t row_pitch_bytes, uint32_t box_rows);
+
+// bf16 NHWC activation [B, H, W, C] for implicit-GEMM convolution: box = [1, box_h, box_w, 64 ch];
+// out-of-bounds coordinates (the conv halo) are zero-filled by the TMA unit.
+int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                   uint32_t box_h, uint32_t box_w);
+
+int sm_count();
+
+}  // namespace spg
