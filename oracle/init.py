@@ -1,0 +1,167 @@
+"""Seeded "spread" random initialisation in the reference's parameter schema -- ORACLE / fixtures only.
+
+PyTorch's default init gives an almost constant output mask (logit range -0.081..-0.077, SURVEY.md
+section 0 item 9), which makes a "1e-2 after sigmoid" parity check vacuous.  This recipe draws every
+tensor from a per-key seeded CPU generator (so it is independent of module construction order and
+reproducible on any box with the same torch build) with scales chosen so that activations stay O(1),
+attention logits have unit spread, BatchNorm statistics are non-trivial and the final logits have a
+standard deviation of a few units.
+"""
+from __future__ import annotations
+
+import hashlib
+import math
+from typing import Dict
+
+import torch
+
+from .hiera import HieraConfig, block_specs
+
+# multipliers on the 1x1 prediction / edge heads, calibrated once so that the logit std is ~2-3
+HEAD_GAIN = {"decoder.pred_heads.0": 6.0, "decoder.pred_heads.1": 4.8, "decoder.pred_heads.2": 3.5,
+             "edge_detector.edge_conv": 4.8}
+# ... and biases that re-centre the logits (post-ReLU channel means shift them by several units)
+HEAD_BIAS = {"decoder.pred_heads.0.bias": -0.94, "decoder.pred_heads.1.bias": 12.1,
+             "decoder.pred_heads.2.bias": -12.6, "edge_detector.edge_conv.bias": 10.3}
+
+
+def _gen(seed: int, key: str) -> torch.Generator:
+    h = hashlib.sha256(f"{seed}:{key}".encode()).digest()
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int.from_bytes(h[:8], "little") & 0x7FFFFFFFFFFFFFFF)
+    return g
+
+
+def _normal(shape, std, g):
+    return torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=g)
+
+
+def _uniform(shape, lo, hi, g):
+    return torch.empty(shape, dtype=torch.float32).uniform_(lo, hi, generator=g)
+
+
+def trunk_shapes(cfg: HieraConfig = HieraConfig()) -> Dict[str, tuple]:
+    d0 = cfg.embed_dim
+    shapes = {
+        "patch_embed.proj.weight": (d0, 3, 7, 7), "patch_embed.proj.bias": (d0,),
+        "pos_embed": (1, d0, *cfg.window_pos_embed_bkg_spatial_size),
+        "pos_embed_window": (1, d0, cfg.window_spec[0], cfg.window_spec[0]),
+    }
+    for s in block_specs(cfg):
+        p = f"blocks.{s.index}."
+        hid = int(s.dim_out * cfg.mlp_ratio)
+        shapes.update({
+            p + "norm1.weight": (s.dim_in,), p + "norm1.bias": (s.dim_in,),
+            p + "attn.qkv.weight": (3 * s.dim_out, s.dim_in), p + "attn.qkv.bias": (3 * s.dim_out,),
+            p + "attn.proj.weight": (s.dim_out, s.dim_out), p + "attn.proj.bias": (s.dim_out,),
+            p + "norm2.weight": (s.dim_out,), p + "norm2.bias": (s.dim_out,),
+            p + "mlp.layers.0.weight": (hid, s.dim_out), p + "mlp.layers.0.bias": (hid,),
+            p + "mlp.layers.1.weight": (s.dim_out, hid), p + "mlp.layers.1.bias": (s.dim_out,),
+        })
+        if s.dim_in != s.dim_out:
+            shapes.update({p + "proj.weight": (s.dim_out, s.dim_in), p + "proj.bias": (s.dim_out,)})
+    return shapes
+
+
+def head_shapes(enc=(288, 576, 1152)) -> Dict[str, tuple]:
+    """Parameter + buffer shapes of fusion / context / edge_detector / decoder."""
+    sh: Dict[str, tuple] = {}
+
+    def bn(pre, c):
+        sh.update({pre + "weight": (c,), pre + "bias": (c,), pre + "running_mean": (c,),
+                   pre + "running_var": (c,), pre + "num_batches_tracked": ()})
+
+    sh["fusion.conv1x1.weight"] = (512, sum(enc), 1, 1)
+    bn("fusion.bn.", 512)
+    sh["fusion.se_block.fc.0.weight"] = (32, 512)
+    sh["fusion.se_block.fc.2.weight"] = (512, 32)
+    sh["context.reduce.0.weight"] = (128, 512, 1, 1)
+    bn("context.reduce.1.", 128)
+    for i in range(4):
+        sh[f"context.branches.{i}.0.weight"] = (128, 1, 3, 3)
+        bn(f"context.branches.{i}.1.", 128)
+    sh["context.global_branch.1.weight"] = (128, 128, 1, 1)
+    bn("context.global_branch.2.", 128)
+    sh["context.fusion.0.weight"] = (128, 5, 1, 1)
+    bn("context.fusion.1.", 128)
+    sh["context.expand.0.weight"] = (256, 128, 1, 1)
+    bn("context.expand.1.", 256)
+    sh["edge_detector.conv1.weight"] = (64, 256, 3, 3)
+    bn("edge_detector.bn1.", 64)
+    sh["edge_detector.edge_conv.weight"] = (1, 64, 1, 1)
+    sh["edge_detector.edge_conv.bias"] = (1,)
+    cin = [320, 320, 128]
+    cout = [256, 128, 64]
+    for i in range(3):
+        p = f"decoder.decoder_blocks.{i}."
+        sh[p + "conv1.weight"] = (cout[i], cin[i], 3, 3)
+        sh[p + "conv1.bias"] = (cout[i],)
+        bn(p + "bn1.", cout[i])
+        sh[p + "conv2.weight"] = (cout[i], cout[i], 3, 3)
+        sh[p + "conv2.bias"] = (cout[i],)
+        bn(p + "bn2.", cout[i])
+        sh[f"decoder.pred_heads.{i}.weight"] = (1, cout[i], 1, 1)
+        sh[f"decoder.pred_heads.{i}.bias"] = (1,)
+    return sh
+
+
+def _draw(key: str, shape: tuple, seed: int) -> torch.Tensor:
+    g = _gen(seed, key)
+    leaf = key.rsplit(".", 1)[-1]
+    if leaf == "num_batches_tracked":
+        return torch.zeros((), dtype=torch.long)
+    if key in HEAD_BIAS:
+        return torch.full(shape, HEAD_BIAS[key], dtype=torch.float32)
+    if key.endswith("pos_embed") or key.endswith("pos_embed_window"):
+        return _normal(shape, 0.25, g)
+    is_norm = ".norm1." in key or ".norm2." in key or ".bn" in key or (
+        leaf in ("running_mean", "running_var")) or _is_bn_key(key)
+    if is_norm:
+        if leaf == "weight":
+            return _uniform(shape, 0.5, 1.5, g)
+        if leaf == "running_var":
+            return _uniform(shape, 0.5, 1.5, g)
+        return _normal(shape, 0.1, g)  # bias / running_mean
+    if leaf == "bias":
+        return _normal(shape, 0.1, g)
+    # weights of conv / linear layers
+    fan_in = 1
+    for d in shape[1:]:
+        fan_in *= d
+    if "encoder.encoder." in key or key.startswith("blocks.") or key.startswith("patch_embed."):
+        gain = 1.0
+        if ".attn.proj." in key or ".mlp.layers.1." in key:
+            gain = 0.5  # residual branches
+        return _normal(shape, gain / math.sqrt(fan_in), g)
+    for name, mult in HEAD_GAIN.items():
+        if key.startswith(name):
+            w = _normal(shape, 1.0 / math.sqrt(fan_in), g)
+            return (w - w.mean()) * mult  # zero-sum head: post-ReLU channel means do not shift the logits
+    if "se_block" in key:
+        return _normal(shape, 1.0 / math.sqrt(fan_in), g)
+    return _normal(shape, math.sqrt(2.0 / fan_in), g)  # ReLU layers
+
+
+_BN_PREFIXES = ("fusion.bn.", "context.reduce.1.", "context.global_branch.2.", "context.fusion.1.",
+                "context.expand.1.", "edge_detector.bn1.")
+
+
+def _is_bn_key(key: str) -> bool:
+    if any(key.startswith(p) for p in _BN_PREFIXES):
+        return True
+    if key.startswith("context.branches.") and key.split(".")[3] == "1":
+        return True
+    return key.startswith("decoder.decoder_blocks.") and key.split(".")[3] in ("bn1", "bn2")
+
+
+def spread_state_dict(seed: int = 0, cfg: HieraConfig = HieraConfig(), trunk_prefix: str = "encoder.encoder.",
+                      enc=None) -> Dict[str, torch.Tensor]:
+    """Full SPEGNet state dict (reference key names, models/spegnet.py:94-135) with the spread init."""
+    dims = cfg.stage_dims
+    enc = tuple(dims[1:4]) if enc is None else enc
+    sd: Dict[str, torch.Tensor] = {}
+    for k, shp in trunk_shapes(cfg).items():
+        sd[trunk_prefix + k] = _draw(trunk_prefix + k, shp, seed)
+    for k, shp in head_shapes(enc).items():
+        sd[k] = _draw(k, shp, seed)
+    return sd
