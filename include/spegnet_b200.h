@@ -11,8 +11,11 @@
  *   - plain device pointers + sizes, caller-owned memory, NO allocation, NO synchronisation and NO
  *     global state inside; work is enqueued on `stream` (a cudaStream_t passed as void*).
  *   - return SPG_OK (0) or a negative SPG_ERR_* code; spg_last_error() gives the text (thread-local).
- *   - activations are NHWC ("tokens x channels") bf16 unless stated; the residual stream and all
- *     logits are fp32; accumulation is fp32 (TMEM).
+ *   - activations are NHWC ("tokens x channels") in the library's 16-bit storage type "h16" unless
+ *     stated: IEEE half in libspegnet_b200_fp16.so, bfloat16 in libspegnet_b200_bf16.so (same sources,
+ *     same entry points, spg_half_is_fp16() tells which; both use kind::f16 tcgen05 MMAs at the same
+ *     rate).  Comments below say "bf16" for brevity.  The residual stream and all logits are fp32;
+ *     accumulation is fp32 (TMEM).
  *   - pointers handed to TMA-fed kernels (GEMM / conv operands) must be 16-byte aligned with a
  *     row pitch that is a multiple of 16 bytes.
  */
@@ -35,7 +38,7 @@ extern "C" {
 #define SPG_ACT_RELU 1
 #define SPG_ACT_GELU 2 /* exact erf GELU, as torch.nn.GELU() in the sam2 trunk MLP */
 
-#define SPG_BF16 0
+#define SPG_H16 0 /* the library's 16-bit storage type (fp16 or bf16, see above) */
 #define SPG_F32 1
 
 typedef void* spg_stream_t; /* cudaStream_t */
@@ -46,6 +49,8 @@ int spg_version(void);
 const char* spg_last_error(void);
 /* SPG_OK iff the current CUDA device is compute capability 10.x (B200). */
 int spg_device_check(void);
+/* 1 if this build stores activations / weights as IEEE fp16, 0 if bfloat16. */
+int spg_half_is_fp16(void);
 /* Number of kernels this library has launched since load / since the last reset (all threads). */
 long long spg_launch_count(void);
 void spg_launch_count_reset(void);
@@ -62,7 +67,7 @@ typedef struct spg_epilogue {
     const float* residual; /* fp32 [M, N] (or [res_rows, N]) or NULL; may alias `out` when out is fp32 */
     int res_rows;          /* 0: one residual row per output row; >0: row index modulo res_rows */
     void* out;             /* [M, N] row-major, bf16 or fp32; NULL = do not store (head only) */
-    int out_dtype;         /* SPG_BF16 / SPG_F32 */
+    int out_dtype;         /* SPG_H16 / SPG_F32 */
     const float* head_w;   /* [N] fp32 or NULL; needs N <= 256 and N % 16 == 0 */
     float head_b;
     float* head_out;       /* [M] fp32 */
@@ -75,7 +80,7 @@ typedef struct spg_epilogue {
  * of the head (models/feature_integration.py:198,239-241,310-314,363-367).
  * K and N may be any multiple of 8 / 16; K tails are zero-filled by TMA.
  */
-int spg_linear_bf16(const void* A, const void* W, int M, int N, int K, const spg_epilogue_t* ep,
+int spg_linear_h16(const void* A, const void* W, int M, int N, int K, const spg_epilogue_t* ep,
                     spg_stream_t stream);
 
 /*
@@ -85,8 +90,89 @@ int spg_linear_bf16(const void* A, const void* W, int M, int N, int K, const spg
  * Replaces nn.Conv2d(k=3,p=1) + BatchNorm2d(eval) + ReLU in EdgeDetectionModule and DecoderBlock
  * (models/object_detection.py:115-123,150-152,193-198,230-236).
  */
-int spg_conv3x3_bf16(const void* x, const void* w, int B, int H, int W, int Cin, int Cout,
+int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, int Cout,
                      const spg_epilogue_t* ep, spg_stream_t stream);
+
+/*
+ * y[M,C] (bf16) = LayerNorm(x[M,C] (fp32 residual stream)) * gamma + beta, eps as given (1e-6 in Hiera).
+ * Replaces blocks.{i}.norm1 / norm2 (HF:modeling_sam2.py:495,528).  C % 4 == 0, C <= 1152.
+ */
+int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
+                           float eps, spg_stream_t stream);
+
+/*
+ * im2col for the 7x7 / stride 4 / pad 3 patch embedding: x fp32 NCHW [B,3,S,S] -> cols bf16
+ * [B*(S/4)^2, 160], column k = c*49 + ky*7 + kx for k < 147, zero above.  The projection itself is
+ * spg_linear_h16 with the positional embedding as a broadcast residual (res_rows = (S/4)^2).
+ * Replaces PatchEmbed's Conv2d(3,144,7,4,3) + permute (HF:modeling_sam2.py:138-148).
+ */
+int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_stream_t stream);
+
+/* 2x2 / stride-2 max pool of an fp32 NHWC map: the pooled shortcut of blocks 2 / 8 / 44
+ * (do_pool(self.proj(x)), HF:modeling_sam2.py:271-279,499-500). */
+int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W, int C, spg_stream_t stream);
+
+/* fp32 -> bf16 copy (stage outputs of the residual stream become GEMM operands of the head). n % 8 == 0. */
+int spg_cast_f32_h16(const float* x, void* y, long long n, spg_stream_t stream);
+
+/*
+ * Multi-head attention over non-overlapping window x window token tiles of the NHWC grid [B,H,W]
+ * (window = 0: global), head_dim 72, softmax scale 1/sqrt(72).  qkv is the fused projection output
+ * bf16 [B*H*W, 3*D] with columns ordered [q|k|v][head][72]; with q_pool the queries are 2x2 max-pooled
+ * inside each window and `out` is the [B, H/2, W/2, D] grid.  Window partition, q-pool and
+ * un-partition are addressing only.  Replaces window_partition / MultiScaleAttention / window_unpartition
+ * (HF:modeling_sam2.py:307-345,378-438,503-525).
+ */
+int spg_window_attention_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads, int window,
+                              int q_pool, spg_stream_t stream);
+
+/*
+ * out[b,y,x,:] = concat(bilinear(src0 [B,h0,w0,c0]), bilinear(src1 [B,h1,w1,c1])) resized to Ho x Wo,
+ * align_corners=False, bf16 NHWC; src1 may be NULL with c1 = 0.  Replaces F.interpolate + torch.cat in
+ * DecoderBlock.forward (models/object_detection.py:219-227).  Channel counts % 8 == 0.
+ */
+int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0, const void* src1, int h1, int w1, int c1,
+                             void* out, int B, int Ho, int Wo, spg_stream_t stream);
+
+/*
+ * CFI fusion tail.  Conv1x1(concat(f2, up2(f3), up4(f4))) is linear, so the three per-scale products
+ * g2 [B,Hs,Hs,C], g3 [B,Hs/2,Hs/2,C], g4 [B,Hs/4,Hs/4,C] (fp32, BatchNorm scale folded into the weights)
+ * are computed at native resolution by spg_linear_h16 and combined here:
+ *   fused = relu(g2 + up2(g3) + up4(g4) + bias)   (bf16 NHWC),  row_sums[b,y,:] = sum_x fused[b,y,x,:]
+ * Replaces F.interpolate x2 + torch.cat + conv1x1 + bn + relu (models/feature_integration.py:229-241)
+ * with 4x fewer MACs and no 2016-channel concat; row_sums feeds the SE squeeze (:147).
+ */
+int spg_fusion_combine(const float* g2, const float* g3, const float* g4, const float* bias, void* fused,
+                       float* row_sums, int B, int Hs, int C, spg_stream_t stream);
+
+/* row_sums[b,y,:] = sum_x x[b,y,x,:] for a bf16 NHWC map (AdaptiveAvgPool2d(1) partials,
+ * models/feature_integration.py:336,401). */
+int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C, spg_stream_t stream);
+
+/*
+ * Pooled-vector MLP, one CTA per image.  mean = sum_rows(row_sums) / count, then
+ *   W2 != NULL: out[b, C] = sigmoid(W2[C,R] @ relu(W1[R,C] @ mean (+ b1)))      (SE gate, :121-126,149)
+ *   W2 == NULL: out[b, R] = relu(W1[R,C] @ mean + b1)          (e-ASPP global branch, :335-345,401)
+ */
+int spg_pooled_mlp(const float* row_sums, int rows, int count, const float* W1, const float* b1, int R,
+                   const float* W2, float* out, int B, int C, spg_stream_t stream);
+
+/* x[b,p,c] *= gate[b,c] in place, bf16 NHWC (SE rescale, models/feature_integration.py:151). */
+int spg_scale_channels_h16(void* x, const float* gate, int B, int HW, int C, spg_stream_t stream);
+
+/*
+ * e-ASPP core in one pass over x bf16 [B,H,W,128]: four depth-wise dilated 3x3 branches (+BN+ReLU),
+ * the broadcast global branch gvec [B,128], the 640-channel concat and the grouped 1x1 fusion conv
+ * (+BN+ReLU): y[b,y,x,g] = relu(sum_j wf[g][j] * cat[5g+j] + wf_bias[g]), cat[c] = branch[c/128][c%128].
+ * dw is [4][9][128] (tap-major, BN scale folded), dw_bias [4][128], wf [128][5], dilations int[4].
+ * Replaces models/feature_integration.py:397-412.
+ */
+int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, const float* gvec, const float* wf,
+                       const float* wf_bias, void* y, int B, int H, int W, const int* dilations,
+                       spg_stream_t stream);
+
+/* bf16 NHWC [B,HW,C] -> fp32 NCHW [B,C,HW] (materialises `features` entries of the output dict on demand). */
+int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,12 +17,12 @@ import torch
 
 from .hiera import HieraConfig, block_specs
 
-# multipliers on the 1x1 prediction / edge heads, calibrated once so that the logit std is ~2-3
-HEAD_GAIN = {"decoder.pred_heads.0": 6.0, "decoder.pred_heads.1": 4.8, "decoder.pred_heads.2": 3.5,
-             "edge_detector.edge_conv": 4.8}
+# multipliers on the 1x1 prediction / edge heads, calibrated once so that the logit std is ~2
+HEAD_GAIN = {"decoder.pred_heads.0": 4.8, "decoder.pred_heads.1": 3.84, "decoder.pred_heads.2": 2.8,
+             "edge_detector.edge_conv": 3.84}
 # ... and biases that re-centre the logits (post-ReLU channel means shift them by several units)
-HEAD_BIAS = {"decoder.pred_heads.0.bias": -0.94, "decoder.pred_heads.1.bias": 12.1,
-             "decoder.pred_heads.2.bias": -12.6, "edge_detector.edge_conv.bias": 10.3}
+HEAD_BIAS = {"decoder.pred_heads.0.bias": -0.75, "decoder.pred_heads.1.bias": 9.68,
+             "decoder.pred_heads.2.bias": -10.08, "edge_detector.edge_conv.bias": 8.24}
 
 
 def _gen(seed: int, key: str) -> torch.Generator:

@@ -1,0 +1,389 @@
+// Windowed / global multi-head attention of the Hiera trunk (head_dim = 72), flash-style:
+//   out = softmax(q k^T / sqrt(72)) v   per (window, head), optional 2x2 max-pooled queries.
+//
+// Window partition / un-partition (HF:modeling_sam2.py:378-438) and the q-pool (:317-321) are pure
+// addressing here: tokens are gathered straight out of the fused qkv GEMM output [tokens, 3*D] and
+// the context is scattered to its final token position, nothing is permuted or copied in HBM.
+//
+// Round-1 implementation: warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) with K / V of the
+// window staged once per CTA in shared memory by cp.async, online softmax in registers.  Attention is
+// 4.7 % of the model's FLOPs; moving it to tcgen05 is listed as next work in DESIGN.md.
+#include <atomic>
+
+#include "common.h"
+#include "half16.cuh"
+
+namespace spg {
+extern std::atomic<long long> g_launches;
+namespace {
+
+constexpr int kHd = 72;          // head dim
+constexpr int kRowsSmem = 256;   // keys staged per CTA pass
+constexpr int kThreads = 128;    // 4 warps x 16 query rows
+
+struct AttnParams {
+    const h16* qkv;  // [B*H*W, 3*D]
+    h16* out;        // [B*Ho*Wo, D]
+    int B, H, W, D, heads;
+    int ws;      // window edge (tokens); global attention = ws == H == W
+    int qpool;   // 1: queries are 2x2 max-pooled inside the window
+    int nwx, nwy;
+    int Nk, Nq;  // keys / queries per window
+    int wpc;     // windows per CTA (Nq < 64) else 1
+    int qtiles;  // 64-row query tiles per window (Nq >= 64) else 1
+    float scale_log2e;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x1(uint32_t addr, uint32_t& r0) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r0) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                 : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32." SPG_MMA_TYPE "." SPG_MMA_TYPE ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// token index (row of the qkv matrix) of local position `li` inside window `win` of image `b`
+__device__ __forceinline__ long long window_token(const AttnParams& p, int b, int wy, int wx, int li) {
+    const int iy = li / p.ws, ix = li - iy * p.ws;
+    return (static_cast<long long>(b) * p.H + wy * p.ws + iy) * p.W + wx * p.ws + ix;
+}
+
+template <int KB>  // keys consumed per softmax step (16 or 64)
+__global__ void __launch_bounds__(kThreads) window_attention_kernel(const AttnParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    h16* Ks = reinterpret_cast<h16*>(smem);
+    h16* Vs = Ks + kRowsSmem * kHd + 8;
+    const uint32_t Ks_u = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
+    const uint32_t Vs_u = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.y;
+    const int wins_per_img = p.nwx * p.nwy;
+
+    // ---- which windows / query rows this CTA owns
+    int win0, qt;
+    if (p.wpc > 1) {
+        win0 = blockIdx.x * p.wpc;
+        qt = 0;
+    } else {
+        win0 = blockIdx.x / p.qtiles;
+        qt = blockIdx.x - win0 * p.qtiles;
+    }
+    const int my_win = win0 + (p.wpc > 1 ? warp : 0);
+    const int b = my_win / wins_per_img;
+    const int wrem = my_win - b * wins_per_img;
+    const int wy = wrem / p.nwx, wx = wrem - wy * p.nwx;
+    const int q0 = (p.wpc > 1 ? 0 : qt * 64 + warp * 16);  // first query row (window-local) of this warp
+    const bool warp_active = q0 < p.Nq;
+
+    // ---- Q fragments (registers), with the optional 2x2 max pool over the window's token grid
+    uint32_t qa[5][4];
+    const size_t ld = static_cast<size_t>(3) * p.D;
+    {
+        const int wq = p.qpool ? p.ws / 2 : p.ws;  // query grid edge
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int qi = q0 + g + 8 * half;
+            const bool ok = warp_active && qi < p.Nq;
+            const int qy = qi / wq, qx = qi - qy * wq;
+            const h16* src[4];
+            int nsrc = 1;
+            if (p.qpool) {
+                nsrc = 4;
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                    src[s] = p.qkv + window_token(p, b, wy, wx, (2 * qy + (s >> 1)) * p.ws + 2 * qx + (s & 1)) * ld + head * kHd;
+            } else {
+                src[0] = p.qkv + window_token(p, b, wy, wx, qi) * ld + head * kHd;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 5; ++kk) {
+#pragma unroll
+                for (int hi = 0; hi < 2; ++hi) {
+                    const int d = kk * 16 + hi * 8 + 2 * t;
+                    uint32_t v = 0u;
+                    if (ok && d < kHd) {
+                        v = *reinterpret_cast<const uint32_t*>(src[0] + d);
+                        for (int s = 1; s < nsrc; ++s) v = max_h2(v, *reinterpret_cast<const uint32_t*>(src[s] + d));
+                    }
+                    qa[kk][half + 2 * hi] = v;
+                }
+            }
+        }
+    }
+
+    float o[9][4];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+    const int rows_total = p.wpc > 1 ? p.wpc * p.Nk : p.Nk;  // key rows this CTA must see in total
+    for (int kbase = 0; kbase < rows_total; kbase += kRowsSmem) {
+        const int rows = min(kRowsSmem, rows_total - kbase);
+        if (kbase > 0) __syncthreads();  // everyone is done with the previous K/V pass
+        // ---- stage K and V rows: 9 x 16 B per row each
+        for (int idx = threadIdx.x; idx < rows * 18; idx += kThreads) {
+            const int r = idx / 18, j = idx - r * 18;
+            const int rr = kbase + r;  // CTA-level key row
+            int kw = win0, kl = rr;
+            if (p.wpc > 1) {
+                kw = win0 + rr / p.Nk;
+                kl = rr - (rr / p.Nk) * p.Nk;
+            }
+            const int kb_ = kw / wins_per_img;
+            const int kwr = kw - kb_ * wins_per_img;
+            const long long tok = window_token(p, kb_, kwr / p.nwx, kwr % p.nwx, kl);
+            const bool isv = j >= 9;
+            const int jj = isv ? j - 9 : j;
+            const h16* src = p.qkv + tok * ld + (isv ? 2 : 1) * p.D + head * kHd + jj * 8;
+            const uint32_t dst = (isv ? Vs_u : Ks_u) + (r * kHd + jj * 8) * 2;
+            cp_async16(dst, src);
+        }
+        cp_async_wait_all();
+        __syncthreads();
+
+        // ---- this warp's slice of the staged rows
+        int kbeg = 0, kend = rows;
+        if (p.wpc > 1) {
+            kbeg = warp * p.Nk;
+            kend = kbeg + p.Nk;
+        }
+        if (warp_active) {
+            for (int k0 = kbeg; k0 < kend; k0 += KB) {
+                constexpr int NT = KB / 8;
+                float s[NT][4];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+                    const int key = k0 + nt * 8 + (lane & 7);
+                    const uint32_t row_addr = Ks_u + key * (kHd * 2);
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(row_addr + (lane >> 3) * 16, b0, b1, b2, b3);  // dims 0..31
+                    mma_bf16(s[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], b0, b1);
+                    mma_bf16(s[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], b2, b3);
+                    ldsm_x4(row_addr + 64 + (lane >> 3) * 16, b0, b1, b2, b3);  // dims 32..63
+                    mma_bf16(s[nt], qa[2][0], qa[2][1], qa[2][2], qa[2][3], b0, b1);
+                    mma_bf16(s[nt], qa[3][0], qa[3][1], qa[3][2], qa[3][3], b2, b3);
+                    ldsm_x1(row_addr + 128, b0);  // dims 64..71; dims 72..79 are zero padding
+                    mma_bf16(s[nt], qa[4][0], qa[4][1], qa[4][2], qa[4][3], b0, 0u);
+                }
+                // ---- online softmax (rows g and g+8)
+                float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+                    mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+                }
+                float corr[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+                    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+                    const float m_new = fmaxf(m_run[h], mx[h] * p.scale_log2e);
+                    corr[h] = exp2f(m_run[h] - m_new);
+                    m_run[h] = m_new;
+                }
+                float rs[2] = {0.f, 0.f};
+                uint32_t pa[NT][2];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const float p0 = exp2f(s[nt][0] * p.scale_log2e - m_run[0]);
+                    const float p1 = exp2f(s[nt][1] * p.scale_log2e - m_run[0]);
+                    const float p2 = exp2f(s[nt][2] * p.scale_log2e - m_run[1]);
+                    const float p3 = exp2f(s[nt][3] * p.scale_log2e - m_run[1]);
+                    rs[0] += p0 + p1;
+                    rs[1] += p2 + p3;
+                    pa[nt][0] = pack2(p0, p1);
+                    pa[nt][1] = pack2(p2, p3);
+                }
+                l_run[0] = l_run[0] * corr[0] + rs[0];
+                l_run[1] = l_run[1] * corr[1] + rs[1];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    o[i][0] *= corr[0]; o[i][1] *= corr[0];
+                    o[i][2] *= corr[1]; o[i][3] *= corr[1];
+                }
+                // ---- O += P V   (k = keys in steps of 16, n = 72 dims in 9 tiles of 8)
+#pragma unroll
+                for (int j = 0; j < KB / 16; ++j) {
+                    const uint32_t a0 = pa[2 * j][0], a1 = pa[2 * j][1], a2 = pa[2 * j + 1][0], a3 = pa[2 * j + 1][1];
+                    const int key = k0 + 16 * j + ((lane >> 3) & 1) * 8 + (lane & 7);
+                    const uint32_t row_addr = Vs_u + key * (kHd * 2) + (lane >> 4) * 16;
+#pragma unroll
+                    for (int dt = 0; dt < 4; ++dt) {
+                        uint32_t b0, b1, b2, b3;
+                        ldsm_x4_t(row_addr + dt * 32, b0, b1, b2, b3);
+                        mma_bf16(o[2 * dt], a0, a1, a2, a3, b0, b1);
+                        mma_bf16(o[2 * dt + 1], a0, a1, a2, a3, b2, b3);
+                    }
+                    uint32_t b0, b1;
+                    ldsm_x2_t(Vs_u + key * (kHd * 2) + 128, b0, b1);
+                    mma_bf16(o[8], a0, a1, a2, a3, b0, b1);
+                }
+            }
+        }
+    }
+
+    if (!warp_active) return;
+    // ---- normalise and scatter to the token's final position
+    const int wq = p.qpool ? p.ws / 2 : p.ws;
+    const int Wo = p.qpool ? p.W / 2 : p.W, Ho = p.qpool ? p.H / 2 : p.H;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float l = l_run[half];
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        const int qi = q0 + g + 8 * half;
+        if (qi >= p.Nq) continue;
+        const float inv = 1.f / l;
+        const int qy = qi / wq, qx = qi - qy * wq;
+        const long long tok = (static_cast<long long>(b) * Ho + wy * wq + qy) * Wo + wx * wq + qx;
+        h16* dst = p.out + tok * p.D + head * kHd + 2 * t;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            *reinterpret_cast<uint32_t*>(dst + 8 * i) = pack2(o[i][2 * half] * inv, o[i][2 * half + 1] * inv);
+    }
+}
+
+// Tiny-window fallback on CUDA cores (block 8 of Hiera-L: 4 pooled queries x 16 keys per window):
+// one warp per (window, head, query), lanes over keys for the scores and over dims for the output.
+__global__ void __launch_bounds__(128) tiny_attention_kernel(const AttnParams p) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total = p.B * p.nwx * p.nwy * p.heads * p.Nq;
+    if (warp_global >= total) return;
+    const int qi = warp_global % p.Nq;
+    const int head = (warp_global / p.Nq) % p.heads;
+    const int win = warp_global / (p.Nq * p.heads);
+    const int wins_per_img = p.nwx * p.nwy;
+    const int b = win / wins_per_img, wrem = win % wins_per_img;
+    const int wy = wrem / p.nwx, wx = wrem % p.nwx;
+    const size_t ld = static_cast<size_t>(3) * p.D;
+    const int wq = p.qpool ? p.ws / 2 : p.ws;
+    const int qy = qi / wq, qx = qi % wq;
+    // q (pooled) : lanes hold dims lane, lane+32, lane+64
+    float q[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int d = lane + 32 * i;
+        float v = 0.f;
+        if (d < kHd) {
+            if (p.qpool) {
+                v = -INFINITY;
+                for (int s = 0; s < 4; ++s)
+                    v = fmaxf(v, h_to_float(p.qkv[window_token(p, b, wy, wx, (2 * qy + (s >> 1)) * p.ws + 2 * qx + (s & 1)) * ld + head * kHd + d]));
+            } else {
+                v = h_to_float(p.qkv[window_token(p, b, wy, wx, qi) * ld + head * kHd + d]);
+            }
+        }
+        q[i] = v;
+    }
+    float m = -INFINITY, l = 0.f, acc[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < p.Nk; ++k) {
+        const h16* kr = p.qkv + window_token(p, b, wy, wx, k) * ld + p.D + head * kHd;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int d = lane + 32 * i;
+            if (d < kHd) s += q[i] * h_to_float(kr[d]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s *= p.scale_log2e;
+        const float m_new = fmaxf(m, s);
+        const float corr = exp2f(m - m_new), pr = exp2f(s - m_new);
+        // probabilities are rounded to bf16 before P.V, like the tensor-core path
+        const float prb = h_to_float(float_to_h(pr));
+        l = l * corr + pr;
+        const h16* vr = kr + p.D;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int d = lane + 32 * i;
+            acc[i] = acc[i] * corr + (d < kHd ? prb * h_to_float(vr[d]) : 0.f);
+        }
+        m = m_new;
+    }
+    const int Wo = p.qpool ? p.W / 2 : p.W, Ho = p.qpool ? p.H / 2 : p.H;
+    const long long tok = (static_cast<long long>(b) * Ho + wy * wq + qy) * Wo + wx * wq + qx;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int d = lane + 32 * i;
+        if (d < kHd) p.out[tok * p.D + head * kHd + d] = float_to_h(acc[i] / l);
+    }
+}
+
+}  // namespace
+}  // namespace spg
+
+extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads,
+                                         int window, int q_pool, spg_stream_t stream) {
+    using namespace spg;
+    SPG_CHECK_ARG(qkv && out, "null pointer");
+    SPG_CHECK_ARG(heads > 0 && D == heads * kHd, "attention is specialised for head_dim 72 (D=%d heads=%d)", D, heads);
+    int ws = window;
+    if (ws == 0) {
+        SPG_CHECK_ARG(H == W, "global attention needs a square token grid");
+        ws = H;
+    }
+    SPG_CHECK_ARG(H % ws == 0 && W % ws == 0, "token grid %dx%d does not tile into %dx%d windows", H, W, ws, ws);
+    SPG_CHECK_ARG(!q_pool || ws % 2 == 0, "q_pool needs an even window");
+    AttnParams p{};
+    p.qkv = static_cast<const h16*>(qkv);
+    p.out = static_cast<h16*>(out);
+    p.B = B; p.H = H; p.W = W; p.D = D; p.heads = heads; p.ws = ws; p.qpool = q_pool ? 1 : 0;
+    p.nwx = W / ws; p.nwy = H / ws;
+    p.Nk = ws * ws;
+    p.Nq = q_pool ? p.Nk / 4 : p.Nk;
+    p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
+    const int nwin = B * p.nwx * p.nwy;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // tensor-core path: 64-row query tiles over <=256-key passes, or four 16-query windows per CTA
+    const bool big = p.Nq % 64 == 0 && p.Nk % 64 == 0 && (p.Nk <= kRowsSmem || p.Nk % kRowsSmem == 0);
+    const bool quad = p.Nq == 16 && (p.Nk == 16 || p.Nk == 64) && nwin % 4 == 0;
+    const bool mma_ok = big || quad;
+    if (!mma_ok) {
+        const long long warps = static_cast<long long>(nwin) * heads * p.Nq;
+        tiny_attention_kernel<<<static_cast<unsigned>((warps * 32 + 127) / 128), 128, 0, st>>>(p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        SPG_CHECK_LAUNCH();
+        return SPG_OK;
+    }
+    p.wpc = p.Nq < 64 ? 64 / p.Nq : 1;
+    p.qtiles = p.Nq >= 64 ? p.Nq / 64 : 1;
+    const int smem = (2 * kRowsSmem * kHd + 16) * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    dim3 grid(p.wpc > 1 ? nwin / p.wpc : nwin * p.qtiles, heads);
+    if (p.Nk == 16)
+        window_attention_kernel<16><<<grid, kThreads, smem, st>>>(p);
+    else
+        window_attention_kernel<64><<<grid, kThreads, smem, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    SPG_CHECK_LAUNCH();
+    return SPG_OK;
+}

@@ -1,5 +1,6 @@
 // Error plumbing, device queries and TMA tensor-map encoding for libspegnet_b200.so.
 #include "common.h"
+#include "half16.cuh"
 
 #include <atomic>
 #include <cstring>
@@ -62,7 +63,7 @@ int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* 
     if (fn == nullptr) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(SPG_ERR_INVALID, "TMA operand must be 16-byte aligned");
     cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box,
+    CUresult r = fn(out, (kHalfIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), rank, const_cast<void*>(base), dims, strides, box,
                     elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -93,6 +94,8 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
 }  // namespace spg
 
 extern "C" int spg_version(void) { return 100; /* 0.1.0 */ }
+
+extern "C" int spg_half_is_fp16(void) { return spg::kHalfIsFp16; }
 
 extern "C" const char* spg_last_error(void) { return spg::error_buffer(); }
 

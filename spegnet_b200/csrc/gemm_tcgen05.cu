@@ -18,6 +18,7 @@
 #include <atomic>
 
 #include "common.h"
+#include "half16.cuh"
 #include "ptx.cuh"
 
 namespace spg {
@@ -60,11 +61,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { return pack2(lo, hi); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
@@ -315,7 +312,7 @@ int fill_epilogue(GemmArgs& a, const spg_epilogue_t* ep, int N) {
     SPG_CHECK_ARG(ep != nullptr, "epilogue descriptor is NULL");
     SPG_CHECK_ARG(ep->out != nullptr || ep->head_out != nullptr, "epilogue has neither out nor head_out");
     SPG_CHECK_ARG(ep->act >= SPG_ACT_NONE && ep->act <= SPG_ACT_GELU, "unknown activation %d", ep->act);
-    SPG_CHECK_ARG(ep->out_dtype == SPG_BF16 || ep->out_dtype == SPG_F32, "unknown out_dtype %d", ep->out_dtype);
+    SPG_CHECK_ARG(ep->out_dtype == SPG_H16 || ep->out_dtype == SPG_F32, "unknown out_dtype %d", ep->out_dtype);
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->out) & 15) == 0, "out must be 16-byte aligned");
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0, "bias must be 16-byte aligned");
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0, "residual must be 16-byte aligned");
@@ -340,7 +337,7 @@ int fill_epilogue(GemmArgs& a, const spg_epilogue_t* ep, int N) {
 }  // namespace
 }  // namespace spg
 
-extern "C" int spg_linear_bf16(const void* A, const void* W, int M, int N, int K,
+extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
                                const spg_epilogue_t* ep, spg_stream_t stream) {
     using namespace spg;
     SPG_CHECK_ARG(A != nullptr && W != nullptr, "A / W is NULL");
@@ -365,7 +362,7 @@ extern "C" int spg_linear_bf16(const void* A, const void* W, int M, int N, int K
     return launch(ta, tb, a, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int spg_conv3x3_bf16(const void* x, const void* w, int B, int H, int W, int Cin, int Cout,
+extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, int Cout,
                                 const spg_epilogue_t* ep, spg_stream_t stream) {
     using namespace spg;
     SPG_CHECK_ARG(x != nullptr && w != nullptr, "x / w is NULL");

@@ -1,0 +1,76 @@
+// The 16-bit storage type of activations and weights is a build-time choice: the same sources build
+// libspegnet_b200_fp16.so (-DSPG_FP16, IEEE half: 10-bit mantissa) and libspegnet_b200_bf16.so (bfloat16:
+// 7-bit mantissa).  Both run kind::f16 tcgen05 MMAs at the same rate with fp32 accumulation; only the
+// operand format bits, the pack / unpack conversions and the mma.sync type differ.
+#pragma once
+#include <cstdint>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace spg {
+
+#ifdef SPG_FP16
+using h16 = __half;
+using h162 = __half2;
+constexpr int kHalfIsFp16 = 1;
+#define SPG_MMA_TYPE "f16"
+#else
+using h16 = __nv_bfloat16;
+using h162 = __nv_bfloat162;
+constexpr int kHalfIsFp16 = 0;
+#define SPG_MMA_TYPE "bf16"
+#endif
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    uint32_t r;
+#ifdef SPG_FP16
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#else
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+#endif
+    return r;
+}
+__device__ __forceinline__ float h_lo(uint32_t u) {
+#ifdef SPG_FP16
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(u & 0xFFFFu)));
+#else
+    return __uint_as_float(u << 16);
+#endif
+}
+__device__ __forceinline__ float h_hi(uint32_t u) {
+#ifdef SPG_FP16
+    return __half2float(__ushort_as_half(static_cast<unsigned short>(u >> 16)));
+#else
+    return __uint_as_float(u & 0xFFFF0000u);
+#endif
+}
+__device__ __forceinline__ float h_to_float(uint16_t u) { return h_lo(u); }
+__device__ __forceinline__ float h_to_float(h16 v) {
+#ifdef SPG_FP16
+    return __half2float(v);
+#else
+    return __bfloat162float(v);
+#endif
+}
+__device__ __forceinline__ h16 float_to_h(float f) {
+#ifdef SPG_FP16
+    return __float2half_rn(f);
+#else
+    return __float2bfloat16(f);
+#endif
+}
+__device__ __forceinline__ uint32_t max_h2(uint32_t a, uint32_t b) {
+    h162 x = *reinterpret_cast<h162*>(&a), y = *reinterpret_cast<h162*>(&b);
+    h162 m = __hmax2(x, y);
+    return *reinterpret_cast<uint32_t*>(&m);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = h_lo(u.x); f[1] = h_hi(u.x); f[2] = h_lo(u.y); f[3] = h_hi(u.y);
+    f[4] = h_lo(u.z); f[5] = h_hi(u.z); f[6] = h_lo(u.w); f[7] = h_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+
+}  // namespace spg

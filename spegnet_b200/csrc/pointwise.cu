@@ -1,0 +1,494 @@
+// HBM-bound kernels of the SPEGNet forward: everything that is not a GEMM / conv / attention.
+// All are vectorised (8 or 16 bytes per access), coalesced over the channel (innermost NHWC) axis and
+// keep their arithmetic in fp32.  Entry points are declared in include/spegnet_b200.h.
+#include <atomic>
+
+#include "common.h"
+#include "half16.cuh"
+
+namespace spg {
+extern std::atomic<long long> g_launches;
+
+namespace {
+
+#define SPG_LAUNCHED()                                        \
+    do {                                                      \
+        g_launches.fetch_add(1, std::memory_order_relaxed);   \
+        SPG_CHECK_LAUNCH();                                   \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the channel axis: fp32 residual stream in, bf16 GEMM operand out. One warp per token,
+// the row lives in registers (two-pass variance), C <= 1152.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnMaxVec = 9;  // 9 float4 per lane * 32 lanes * 4 = 1152 channels
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, uint16_t* __restrict__ y,
+                                                        int M, int C, float eps) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    const int nvec = C >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
+    float4 v[kLnMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            v[i] = xr[j];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * C);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int i = 0; i < kLnMaxVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+            yr[j] = make_uint2(pack2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
+                               pack2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patchify: NCHW fp32 image -> im2col rows for the 7x7 / stride 4 / pad 3 patch embedding,
+// k = c*49 + ky*7 + kx, zero-padded from 147 to 160 columns (bf16). One thread per (row, 8 columns).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, uint16_t* __restrict__ cols, int B,
+                                                       int S) {
+    const int G = S >> 2;
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    const long long total = static_cast<long long>(B) * G * G * 20;
+    if (idx >= total) return;
+    const int kv = idx % 20;
+    const long long row = idx / 20;
+    const int ox = row % G, oy = (row / G) % G, b = row / (static_cast<long long>(G) * G);
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = kv * 8 + i;
+        float val = 0.f;
+        if (k < 147) {
+            const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+            const int iy = oy * 4 + ky - 3, ix = ox * 4 + kx - 3;
+            if (iy >= 0 && iy < S && ix >= 0 && ix < S)
+                val = __ldg(x + ((static_cast<size_t>(b) * 3 + c) * S + iy) * S + ix);
+        }
+        f[i] = val;
+    }
+    reinterpret_cast<uint4*>(cols)[idx] = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 / stride 2 max pool on an fp32 NHWC map (the pooled shortcut of blocks 2 / 8 / 44).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H,
+                                                      int W, int C4) {
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    const long long total = static_cast<long long>(B) * Ho * Wo * C4;
+    if (idx >= total) return;
+    const int c = idx % C4;
+    const long long p = idx / C4;
+    const int ox = p % Wo, oy = (p / Wo) % Ho, b = p / (static_cast<long long>(Wo) * Ho);
+    const size_t base = ((static_cast<size_t>(b) * H + 2 * oy) * W + 2 * ox) * C4 + c;
+    const float4 a = x[base], bb = x[base + C4], cc = x[base + static_cast<size_t>(W) * C4],
+                 d = x[base + static_cast<size_t>(W) * C4 + C4];
+    y[idx] = make_float4(fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)), fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y)),
+                         fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)), fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w)));
+}
+
+// fp32 -> bf16 cast, 8 elements per thread.
+__global__ void __launch_bounds__(256) cast_kernel(const float4* __restrict__ x, uint4* __restrict__ y, long long n8) {
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= n8) return;
+    const float4 a = x[2 * idx], b = x[2 * idx + 1];
+    y[idx] = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Bilinear (align_corners=False) source coordinates exactly as ATen's upsample_bilinear2d:
+// src = max(0, (dst + 0.5) * in/out - 0.5), i1 = min(i0 + 1, in - 1).
+// ------------------------------------------------------------------------------------------------
+struct Lerp {
+    int i0, i1;
+    float w0, w1;
+};
+__device__ __forceinline__ Lerp lerp_coord(int dst, int in, int out) {
+    const float scale = static_cast<float>(in) / static_cast<float>(out);
+    float src = (dst + 0.5f) * scale - 0.5f;
+    src = src < 0.f ? 0.f : src;
+    Lerp l;
+    l.i0 = static_cast<int>(src);
+    l.i1 = l.i0 + (l.i0 < in - 1 ? 1 : 0);
+    l.w1 = src - l.i0;
+    l.w0 = 1.f - l.w1;
+    return l;
+}
+
+// out[b,y,x,:] = concat(bilinear(src0)[C0], bilinear(src1)[C1]) in bf16 NHWC; src1 may be absent (C1 = 0).
+// One thread per (pixel, 8 channels).
+__global__ void __launch_bounds__(256)
+upcat_kernel(const uint4* __restrict__ s0, int h0, int w0, int c0v, const uint4* __restrict__ s1, int h1, int w1,
+             int c1v, uint4* __restrict__ out, int B, int Ho, int Wo) {
+    const int cv = c0v + c1v;
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    const long long total = static_cast<long long>(B) * Ho * Wo * cv;
+    if (idx >= total) return;
+    const int c = idx % cv;
+    const long long p = idx / cv;
+    const int ox = p % Wo, oy = (p / Wo) % Ho, b = p / (static_cast<long long>(Wo) * Ho);
+    const uint4* src;
+    int h, w, ncv, cc;
+    if (c < c0v) {
+        src = s0; h = h0; w = w0; ncv = c0v; cc = c;
+    } else {
+        src = s1; h = h1; w = w1; ncv = c1v; cc = c - c0v;
+    }
+    const Lerp ly = lerp_coord(oy, h, Ho), lx = lerp_coord(ox, w, Wo);
+    const size_t img = static_cast<size_t>(b) * h * w;
+    float a[8], bq[8], cq[8], d[8], r[8];
+    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i0) * ncv + cc), a);
+    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i1) * ncv + cc), bq);
+    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i0) * ncv + cc), cq);
+    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i1) * ncv + cc), d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        r[i] = ly.w0 * (lx.w0 * a[i] + lx.w1 * bq[i]) + ly.w1 * (lx.w0 * cq[i] + lx.w1 * d[i]);
+    out[idx] = pack8(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CFI fusion tail.  The 1x1 conv over concat(f2, up2(f3), up4(f4)) is linear, so it is evaluated at
+// each source's native resolution (g2, g3, g4 = per-scale GEMM outputs, fp32, BN scale folded) and
+// combined here: fused = relu(g2 + up2(g3) + up4(g4) + bias).  One CTA per (image, output row);
+// thread = 4 channels, looping over the row's pixels; also emits per-row channel sums for the SE squeeze.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+fusion_combine_kernel(const float4* __restrict__ g2, const float4* __restrict__ g3, const float4* __restrict__ g4,
+                      const float4* __restrict__ bias, uint2* __restrict__ fused, float4* __restrict__ partial, int Hs,
+                      int C4) {
+    const int b = blockIdx.y, y = blockIdx.x;
+    const int H3 = Hs >> 1, H4 = Hs >> 2;
+    const Lerp ly3 = lerp_coord(y, H3, Hs), ly4 = lerp_coord(y, H4, Hs);
+    for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+        const float4 bi = __ldg(bias + c);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int x = 0; x < Hs; ++x) {
+            const Lerp lx3 = lerp_coord(x, H3, Hs), lx4 = lerp_coord(x, H4, Hs);
+            float4 v = g2[((static_cast<size_t>(b) * Hs + y) * Hs + x) * C4 + c];
+            auto bil = [&](const float4* g, int hh, const Lerp& ly, const Lerp& lx) {
+                const size_t img = static_cast<size_t>(b) * hh * hh;
+                const float4 p00 = __ldg(g + (img + ly.i0 * hh + lx.i0) * C4 + c);
+                const float4 p01 = __ldg(g + (img + ly.i0 * hh + lx.i1) * C4 + c);
+                const float4 p10 = __ldg(g + (img + ly.i1 * hh + lx.i0) * C4 + c);
+                const float4 p11 = __ldg(g + (img + ly.i1 * hh + lx.i1) * C4 + c);
+                v.x += ly.w0 * (lx.w0 * p00.x + lx.w1 * p01.x) + ly.w1 * (lx.w0 * p10.x + lx.w1 * p11.x);
+                v.y += ly.w0 * (lx.w0 * p00.y + lx.w1 * p01.y) + ly.w1 * (lx.w0 * p10.y + lx.w1 * p11.y);
+                v.z += ly.w0 * (lx.w0 * p00.z + lx.w1 * p01.z) + ly.w1 * (lx.w0 * p10.z + lx.w1 * p11.z);
+                v.w += ly.w0 * (lx.w0 * p00.w + lx.w1 * p01.w) + ly.w1 * (lx.w0 * p10.w + lx.w1 * p11.w);
+            };
+            bil(g3, H3, ly3, lx3);
+            bil(g4, H4, ly4, lx4);
+            v.x = fmaxf(v.x + bi.x, 0.f);
+            v.y = fmaxf(v.y + bi.y, 0.f);
+            v.z = fmaxf(v.z + bi.z, 0.f);
+            v.w = fmaxf(v.w + bi.w, 0.f);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            fused[((static_cast<size_t>(b) * Hs + y) * Hs + x) * C4 + c] = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+        }
+        partial[(static_cast<size_t>(b) * Hs + y) * C4 + c] = acc;
+    }
+}
+
+// Per-row channel sums of a bf16 NHWC map (global-average-pool partials): one CTA per (image, row).
+__global__ void __launch_bounds__(128)
+row_sums_kernel(const uint2* __restrict__ x, float4* __restrict__ partial, int H, int W, int C4) {
+    const int b = blockIdx.y, y = blockIdx.x;
+    for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int xx = 0; xx < W; ++xx) {
+            const uint2 u = x[((static_cast<size_t>(b) * H + y) * W + xx) * C4 + c];
+            acc.x += h_lo(u.x); acc.y += h_hi(u.x); acc.z += h_lo(u.y); acc.w += h_hi(u.y);
+        }
+        partial[(static_cast<size_t>(b) * H + y) * C4 + c] = acc;
+    }
+}
+
+// Squeeze-excite gate (or, with `sigmoid_out`=0 and bias, the e-ASPP global branch): one CTA per image.
+//   mean[c] = sum_rows partial[b,r,c] / count
+//   se:      gate = sigmoid(W2 @ relu(W1 @ mean))           W1 [R,C], W2 [C,R]
+//   global:  out  = relu(W1 @ mean + bias)                  W1 [C,C] (BN folded), W2 == nullptr
+__global__ void __launch_bounds__(512)
+pooled_mlp_kernel(const float* __restrict__ partial, int rows, float inv_count, const float* __restrict__ W1,
+                  const float* __restrict__ b1, int R, const float* __restrict__ W2, float* __restrict__ out, int C) {
+    extern __shared__ float sm[];
+    float* mean = sm;          // [C]
+    float* hidden = sm + C;    // [R]
+    const int b = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < rows; ++r) s += partial[(static_cast<size_t>(b) * rows + r) * C + c];
+        mean[c] = s * inv_count;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < R; j += nwarps) {
+        float s = 0.f;
+        for (int c = lane; c < C; c += 32) s += W1[static_cast<size_t>(j) * C + c] * mean[c];
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (b1 != nullptr) s += b1[j];
+            s = fmaxf(s, 0.f);
+            if (W2 == nullptr) out[static_cast<size_t>(b) * R + j] = s;
+            hidden[j] = s;
+        }
+    }
+    if (W2 == nullptr) return;
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = 0.f;
+        for (int j = 0; j < R; ++j) s += W2[static_cast<size_t>(c) * R + j] * hidden[j];
+        out[static_cast<size_t>(b) * C + c] = 1.f / (1.f + __expf(-s));
+    }
+}
+
+// x[b, p, c] *= gate[b, c]  (bf16 NHWC in place, 8 channels per thread)
+__global__ void __launch_bounds__(256)
+scale_channels_kernel(uint4* __restrict__ x, const float* __restrict__ gate, long long total, int HW, int C8) {
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= total) return;
+    const int c = idx % C8;
+    const long long b = idx / (static_cast<long long>(HW) * C8);
+    float f[8];
+    unpack8(x[idx], f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate + b * C8 * 8) + 2 * c);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate + b * C8 * 8) + 2 * c + 1);
+    f[0] *= g0.x; f[1] *= g0.y; f[2] *= g0.z; f[3] *= g0.w;
+    f[4] *= g1.x; f[5] *= g1.y; f[6] *= g1.z; f[7] *= g1.w;
+    x[idx] = pack8(f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// e-ASPP core: four depth-wise dilated 3x3 branches (+BN+ReLU), the broadcast global branch, the
+// 640-channel concat and the grouped 1x1 "fusion" conv (+BN+ReLU) in ONE pass, nothing materialised.
+// Concat channel c = branch*128 + ch feeds output channel c/5 with weight wf[c/5][c%5]
+// (models/feature_integration.py:349-357,411-412).  One thread owns 40 consecutive concat channels
+// (= five 8-channel vectors, each inside one branch) of one pixel and produces 8 output channels.
+// ------------------------------------------------------------------------------------------------
+struct AsppParams {
+    const uint4* x;        // [B,H,W,128] bf16 (reduce output)
+    const float* dw;       // [4][9][128] depth-wise weights, BN scale folded
+    const float* dw_bias;  // [4][128]
+    const float* gvec;     // [B][128] global branch output (already BN+ReLU)
+    const float* wf;       // [128][5] grouped-conv weights, BN scale folded
+    const float* wf_bias;  // [128]
+    uint4* y;              // [B,H,W,128] bf16
+    int B, H, W;
+    int dil[4];
+};
+
+__global__ void __launch_bounds__(256) aspp_kernel(const AsppParams p) {
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    const long long total = static_cast<long long>(p.B) * p.H * p.W * 16;
+    if (idx >= total) return;
+    const int t = idx & 15;  // which 40-channel slice of the 640-channel concat
+    const long long pix = idx >> 4;
+    const int x0 = pix % p.W, y0 = (pix / p.W) % p.H;
+    const long long b = pix / (static_cast<long long>(p.W) * p.H);
+    float cat[40];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+        const int c0 = 40 * t + 8 * v;
+        const int br = c0 >> 7, ch0 = c0 & 127;
+        float acc[8];
+        if (br == 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = __ldg(p.gvec + b * 128 + ch0 + i);
+        } else {
+            const int d = p.dil[br];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int yy = y0 + (tap / 3 - 1) * d, xx = x0 + (tap % 3 - 1) * d;
+                if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+                float f[8];
+                unpack8(__ldg(p.x + ((b * p.H + yy) * p.W + xx) * 16 + (ch0 >> 3)), f);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.dw + (br * 9 + tap) * 128 + ch0));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.dw + (br * 9 + tap) * 128 + ch0) + 1);
+                acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+                acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+                acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+                acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i] + __ldg(p.dw_bias + br * 128 + ch0 + i), 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cat[8 * v + i] = acc[i];
+    }
+    float o[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        const int go = 8 * t + g;
+        float s = __ldg(p.wf_bias + go);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) s = fmaf(__ldg(p.wf + go * 5 + j), cat[5 * g + j], s);
+        o[g] = fmaxf(s, 0.f);
+    }
+    p.y[pix * 16 + t] = pack8(o);
+}
+
+// bf16 NHWC -> fp32 NCHW (for the lazily materialised `features` entries of the output dict).
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, int HW, int C, long long total) {
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= total) return;
+    const int p = idx % HW;
+    const int c = (idx / HW) % C;
+    const long long b = idx / (static_cast<long long>(HW) * C);
+    y[idx] = h_to_float(x[(b * HW + p) * C + c]);
+}
+
+inline unsigned blocks_for(long long total, int per_block = 256) {
+    return static_cast<unsigned>((total + per_block - 1) / per_block);
+}
+
+}  // namespace
+}  // namespace spg
+
+using namespace spg;
+
+extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
+                                      float eps, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && gamma && beta && y, "null pointer");
+    SPG_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= kLnMaxVec * 128, "LayerNorm needs C %% 4 == 0 and C <= 1152 (C=%d)", C);
+    layernorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, static_cast<uint16_t*>(y), M, C, eps);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && cols, "null pointer");
+    SPG_CHECK_ARG(B > 0 && S > 0 && S % 4 == 0, "bad image size S=%d", S);
+    const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * 20;
+    patchify_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint16_t*>(cols), B, S);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W, int C, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && y, "null pointer");
+    SPG_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool needs even H, W and C %% 4 == 0");
+    const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 4);
+    maxpool_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), B, H, W, C / 4);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_cast_f32_h16(const float* x, void* y, long long n, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && y, "null pointer");
+    SPG_CHECK_ARG(n > 0 && n % 8 == 0, "cast needs n %% 8 == 0");
+    cast_kernel<<<blocks_for(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(x), static_cast<uint4*>(y), n / 8);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0, const void* src1, int h1, int w1,
+                                        int c1, void* out, int B, int Ho, int Wo, spg_stream_t stream) {
+    SPG_CHECK_ARG(src0 && out, "null pointer");
+    SPG_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0 && c0 > 0 && c1 >= 0, "channel counts must be multiples of 8");
+    SPG_CHECK_ARG(c1 == 0 || src1 != nullptr, "src1 is NULL but c1 > 0");
+    const long long total = static_cast<long long>(B) * Ho * Wo * ((c0 + c1) / 8);
+    upcat_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(src0), h0, w0, c0 / 8, static_cast<const uint4*>(src1), h1, w1, c1 / 8,
+        static_cast<uint4*>(out), B, Ho, Wo);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_fusion_combine(const float* g2, const float* g3, const float* g4, const float* bias, void* fused,
+                                  float* row_sums, int B, int Hs, int C, spg_stream_t stream) {
+    SPG_CHECK_ARG(g2 && g3 && g4 && bias && fused && row_sums, "null pointer");
+    SPG_CHECK_ARG(Hs % 4 == 0 && C % 4 == 0, "fusion_combine needs Hs %% 4 == 0 and C %% 4 == 0");
+    fusion_combine_kernel<<<dim3(Hs, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(g2), reinterpret_cast<const float4*>(g3), reinterpret_cast<const float4*>(g4),
+        reinterpret_cast<const float4*>(bias), static_cast<uint2*>(fused), reinterpret_cast<float4*>(row_sums), Hs, C / 4);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && row_sums, "null pointer");
+    SPG_CHECK_ARG(C % 4 == 0, "row_sums needs C %% 4 == 0");
+    row_sums_kernel<<<dim3(H, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint2*>(x), reinterpret_cast<float4*>(row_sums), H, W, C / 4);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_pooled_mlp(const float* row_sums, int rows, int count, const float* W1, const float* b1, int R,
+                              const float* W2, float* out, int B, int C, spg_stream_t stream) {
+    SPG_CHECK_ARG(row_sums && W1 && out, "null pointer");
+    SPG_CHECK_ARG(rows > 0 && count > 0 && R > 0 && C > 0, "bad pooled_mlp shape");
+    pooled_mlp_kernel<<<B, 512, (C + R) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        row_sums, rows, 1.0f / count, W1, b1, R, W2, out, C);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_scale_channels_h16(void* x, const float* gate, int B, int HW, int C, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && gate, "null pointer");
+    SPG_CHECK_ARG(C % 8 == 0, "scale_channels needs C %% 8 == 0");
+    const long long total = static_cast<long long>(B) * HW * (C / 8);
+    scale_channels_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<uint4*>(x), gate, total, HW, C / 8);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, const float* gvec,
+                                  const float* wf, const float* wf_bias, void* y, int B, int H, int W,
+                                  const int* dilations, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && dw && dw_bias && gvec && wf && wf_bias && y && dilations, "null pointer");
+    AsppParams p{static_cast<const uint4*>(x), dw, dw_bias, gvec, wf, wf_bias, static_cast<uint4*>(y), B, H, W,
+                 {dilations[0], dilations[1], dilations[2], dilations[3]}};
+    const long long total = static_cast<long long>(B) * H * W * 16;
+    aspp_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && y, "null pointer");
+    const long long total = static_cast<long long>(B) * HW * C;
+    nhwc_to_nchw_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint16_t*>(x), y, HW, C, total);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}

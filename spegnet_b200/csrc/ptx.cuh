@@ -172,11 +172,17 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n.
+// kind::f16 instruction descriptor: D=f32, A=B=bf16 (or fp16 when built with -DSPG_FP16), both K-major,
+// M=128, N=n.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16_f32(uint32_t m, uint32_t n) {
+#ifdef SPG_FP16
+    constexpr uint32_t kFmt = 0u;  // F16
+#else
+    constexpr uint32_t kFmt = 1u;  // BF16
+#endif
     return (1u << 4)            // c_format = F32
-           | (1u << 7)          // a_format = BF16
-           | (1u << 10)         // b_format = BF16
+           | (kFmt << 7)        // a_format
+           | (kFmt << 10)       // b_format
            | ((n >> 3) << 17)   // n_dim
            | ((m >> 4) << 24);  // m_dim
 }

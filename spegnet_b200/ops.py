@@ -1,0 +1,185 @@
+"""Tensor-level wrappers over the C-ABI (one Python function per ``spg_*`` entry point).
+
+Each wrapper validates dtype / device / contiguity, takes raw ``data_ptr()``s and enqueues on torch's
+current CUDA stream.  No arithmetic happens in Python or in PyTorch ops here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, F32, Epilogue  # noqa: F401
+from ._lib import H16 as OUT_H16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+H16 = "h16"  # marker: a 16-bit operand (fp16 or bf16; selects the library variant)
+
+
+def _lib_for(t: torch.Tensor):
+    """(library, dtype name) for the 16-bit operand `t`."""
+    name = _lib.dtype_name(t.dtype)
+    return _lib.load(name), name
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (spegnet_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if dtype is H16:
+        if t.dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError(f"{name} must be fp16 or bf16, got {t.dtype}")
+    elif dtype is not None and t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out) -> Epilogue:
+    ep = Epilogue()
+    ep.bias = _ptr(bias, torch.float32, "bias")
+    ep.act = act
+    ep.residual = _ptr(residual, torch.float32, "residual")
+    ep.res_rows = res_rows
+    if out is not None:
+        if out.dtype not in (torch.bfloat16, torch.float16, torch.float32):
+            raise ValueError("out must be fp16 / bf16 or fp32")
+        ep.out = _ptr(out, None, "out")
+        ep.out_dtype = F32 if out.dtype == torch.float32 else OUT_H16
+    ep.head_w = _ptr(head_w, torch.float32, "head_w")
+    ep.head_b = float(head_b)
+    ep.head_out = _ptr(head_out, torch.float32, "head_out")
+    return ep
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bias=None, act=ACT_NONE,
+           residual=None, res_rows: int = 0, head_w=None, head_b: float = 0.0, head_out=None) -> None:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; see spg_linear_h16."""
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"weight K {w.shape[1]} != activation K {K}")
+    ep = _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out)
+    lib, dn = _lib_for(a)
+    rc = lib.spg_linear_h16(_ptr(a, H16, "a"), _ptr(w, H16, "w"), M, N, K,
+                                     C.byref(ep), _stream())
+    _lib.check(rc, "spg_linear_h16", dn)
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bias=None, act=ACT_NONE,
+            head_w=None, head_b: float = 0.0, head_out=None) -> None:
+    """x bf16 NHWC [B,H,W,Cin], w bf16 [Cout, 9*Cin] (tap-major); see spg_conv3x3_h16."""
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    if w.shape[1] != 9 * Cin:
+        raise ValueError("conv weight must be [Cout, 9*Cin]")
+    ep = _epilogue(out, bias, act, None, 0, head_w, head_b, head_out)
+    lib, dn = _lib_for(x)
+    rc = lib.spg_conv3x3_h16(_ptr(x, H16, "x"), _ptr(w, H16, "w"), B, H, W, Cin, Cout,
+                                      C.byref(ep), _stream())
+    _lib.check(rc, "spg_conv3x3_h16", dn)
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, eps: float) -> None:
+    M, Cc = x.shape
+    lib, dn = _lib_for(y)
+    rc = lib.spg_layernorm_f32_h16(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                            _ptr(beta, torch.float32, "beta"), _ptr(y, H16, "y"), M, Cc,
+                                            eps, _stream())
+    _lib.check(rc, "spg_layernorm_f32_h16", dn)
+
+
+def patchify(x: torch.Tensor, cols: torch.Tensor) -> None:
+    B, _, S, _ = x.shape
+    lib, dn = _lib_for(cols)
+    rc = lib.spg_patchify_7x7s4(_ptr(x, torch.float32, "x"), _ptr(cols, H16, "cols"), B, S, _stream())
+    _lib.check(rc, "spg_patchify_7x7s4", dn)
+
+
+def maxpool2x2(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, Cc: int) -> None:
+    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    rc = lib.spg_maxpool2x2_f32(_ptr(x, torch.float32, "x"), _ptr(y, torch.float32, "y"), B, H, W, Cc, _stream())
+    _lib.check(rc, "spg_maxpool2x2_f32", dn)
+
+
+def cast_h16(x: torch.Tensor, y: torch.Tensor) -> None:
+    lib, dn = _lib_for(y)
+    rc = lib.spg_cast_f32_h16(_ptr(x, torch.float32, "x"), _ptr(y, H16, "y"), x.numel(), _stream())
+    _lib.check(rc, "spg_cast_f32_h16", dn)
+
+
+def window_attention(qkv: torch.Tensor, out: torch.Tensor, B: int, H: int, W: int, D: int, heads: int, window: int,
+                     q_pool: bool) -> None:
+    lib, dn = _lib_for(qkv)
+    rc = lib.spg_window_attention_h16(_ptr(qkv, H16, "qkv"), _ptr(out, H16, "out"), B,
+                                               H, W, D, heads, window, int(q_pool), _stream())
+    _lib.check(rc, "spg_window_attention_h16", dn)
+
+
+def upsample_concat(src0: torch.Tensor, src1: Optional[torch.Tensor], out: torch.Tensor) -> None:
+    B, Ho, Wo, _ = out.shape
+    _, h0, w0, c0 = src0.shape
+    h1 = w1 = c1 = 0
+    if src1 is not None:
+        _, h1, w1, c1 = src1.shape
+    lib, dn = _lib_for(src0)
+    rc = lib.spg_upsample_concat_h16(_ptr(src0, H16, "src0"), h0, w0, c0,
+                                              _ptr(src1, H16, "src1"), h1, w1, c1,
+                                              _ptr(out, H16, "out"), B, Ho, Wo, _stream())
+    _lib.check(rc, "spg_upsample_concat_h16", dn)
+
+
+def fusion_combine(g2, g3, g4, bias, fused, row_sums, B: int, Hs: int, Cc: int) -> None:
+    lib, dn = _lib_for(fused)
+    rc = lib.spg_fusion_combine(_ptr(g2, torch.float32, "g2"), _ptr(g3, torch.float32, "g3"),
+                                        _ptr(g4, torch.float32, "g4"), _ptr(bias, torch.float32, "bias"),
+                                        _ptr(fused, H16, "fused"), _ptr(row_sums, torch.float32, "row_sums"),
+                                        B, Hs, Cc, _stream())
+    _lib.check(rc, "spg_fusion_combine", dn)
+
+
+def row_sums(x, out, B: int, H: int, W: int, Cc: int) -> None:
+    lib, dn = _lib_for(x)
+    rc = lib.spg_row_sums_h16(_ptr(x, H16, "x"), _ptr(out, torch.float32, "row_sums"), B, H, W, Cc,
+                                       _stream())
+    _lib.check(rc, "spg_row_sums_h16", dn)
+
+
+def pooled_mlp(row_sums_t, rows: int, count: int, w1, b1, R: int, w2, out, B: int, Cc: int) -> None:
+    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    rc = lib.spg_pooled_mlp(_ptr(row_sums_t, torch.float32, "row_sums"), rows, count,
+                                    _ptr(w1, torch.float32, "w1"), _ptr(b1, torch.float32, "b1"), R,
+                                    _ptr(w2, torch.float32, "w2"), _ptr(out, torch.float32, "out"), B, Cc, _stream())
+    _lib.check(rc, "spg_pooled_mlp", dn)
+
+
+def scale_channels(x, gate, B: int, HW: int, Cc: int) -> None:
+    lib, dn = _lib_for(x)
+    rc = lib.spg_scale_channels_h16(_ptr(x, H16, "x"), _ptr(gate, torch.float32, "gate"), B, HW, Cc,
+                                             _stream())
+    _lib.check(rc, "spg_scale_channels_h16", dn)
+
+
+def easpp_branches(x, dw, dw_bias, gvec, wf, wf_bias, y, B: int, H: int, W: int, dilations) -> None:
+    dil = (C.c_int * 4)(*dilations)
+    lib, dn = _lib_for(x)
+    rc = lib.spg_easpp_branches(_ptr(x, H16, "x"), _ptr(dw, torch.float32, "dw"),
+                                        _ptr(dw_bias, torch.float32, "dw_bias"), _ptr(gvec, torch.float32, "gvec"),
+                                        _ptr(wf, torch.float32, "wf"), _ptr(wf_bias, torch.float32, "wf_bias"),
+                                        _ptr(y, H16, "y"), B, H, W, dil, _stream())
+    _lib.check(rc, "spg_easpp_branches", dn)
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor, y: torch.Tensor, B: int, HW: int, Cc: int) -> None:
+    lib, dn = _lib_for(x)
+    rc = lib.spg_nhwc_h16_to_nchw_f32(_ptr(x, H16, "x"), _ptr(y, torch.float32, "y"), B, HW, Cc,
+                                               _stream())
+    _lib.check(rc, "spg_nhwc_h16_to_nchw_f32", dn)

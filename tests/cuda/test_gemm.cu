@@ -1,7 +1,7 @@
 // Standalone GPU check of the tcgen05 GEMM / conv engine against naive CUDA-core reference kernels
 // (no torch: starts in milliseconds on a fresh box).  Prints one line per case with max error and
 // the measured throughput; exit code = number of failed cases.
-//   build: make -C spegnet_b200/csrc test_gemm       run: spegnet_b200/csrc/build/test_gemm [--perf]
+//   build: make -C spegnet_b200/csrc test_gemm       run: spegnet_b200/csrc/build/test_gemm_{fp16,bf16} [--perf]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +9,7 @@
 #include <vector>
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/spegnet_b200.h"
@@ -22,18 +23,31 @@
         }                                                                              \
     } while (0)
 
+// 16-bit storage type follows the library variant this binary is linked against (see half16.cuh)
+#ifdef SPG_FP16
+typedef __half h16;
+static inline h16 to_h16(float f) { return __float2half(f); }
+static inline float from_h16(h16 v) { return __half2float(v); }
+__device__ inline float dev_from_h16(h16 v) { return __half2float(v); }
+#else
+typedef __nv_bfloat16 h16;
+static inline h16 to_h16(float f) { return __float2bfloat16(f); }
+static inline float from_h16(h16 v) { return __bfloat162float(v); }
+__device__ inline float dev_from_h16(h16 v) { return __bfloat162float(v); }
+#endif
+
 static uint32_t g_seed = 12345u;
 static float frand() {
     g_seed = g_seed * 1664525u + 1013904223u;
     return ((g_seed >> 8) & 0xFFFF) / 32768.0f - 1.0f;
 }
 
-static __nv_bfloat16* dev_bf16(size_t n, float scale) {
-    std::vector<__nv_bfloat16> h(n);
-    for (size_t i = 0; i < n; ++i) h[i] = __float2bfloat16(frand() * scale);
-    __nv_bfloat16* d;
-    CK(cudaMalloc(&d, n * sizeof(__nv_bfloat16)));
-    CK(cudaMemcpy(d, h.data(), n * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+static h16* dev_bf16(size_t n, float scale) {
+    std::vector<h16> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = to_h16(frand() * scale);
+    h16* d;
+    CK(cudaMalloc(&d, n * sizeof(h16)));
+    CK(cudaMemcpy(d, h.data(), n * sizeof(h16), cudaMemcpyHostToDevice));
     return d;
 }
 static float* dev_f32(size_t n, float scale) {
@@ -51,20 +65,20 @@ __device__ float ref_act(float v, int act) {
     return v;
 }
 
-__global__ void ref_gemm(const __nv_bfloat16* A, const __nv_bfloat16* W, int M, int N, int K, const float* bias,
+__global__ void ref_gemm(const h16* A, const h16* W, int M, int N, int K, const float* bias,
                          int act, const float* res, int res_rows, float* out) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)M * N) return;
     const int m = idx / N, n = idx % N;
     float acc = 0.f;
-    for (int k = 0; k < K; ++k) acc += __bfloat162float(A[(size_t)m * K + k]) * __bfloat162float(W[(size_t)n * K + k]);
+    for (int k = 0; k < K; ++k) acc += dev_from_h16(A[(size_t)m * K + k]) * dev_from_h16(W[(size_t)n * K + k]);
     if (bias) acc += bias[n];
     acc = ref_act(acc, act);
     if (res) acc += res[(size_t)(res_rows > 0 ? m % res_rows : m) * N + n];
     out[idx] = acc;
 }
 
-__global__ void ref_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wt, int B, int H, int Wd, int Cin, int Cout,
+__global__ void ref_conv(const h16* X, const h16* Wt, int B, int H, int Wd, int Cin, int Cout,
                          const float* bias, int act, float* out) {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (idx >= (long long)B * H * Wd * Cout) return;
@@ -76,9 +90,9 @@ __global__ void ref_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wt, int B,
         for (int kx = 0; kx < 3; ++kx) {
             const int yy = y + ky - 1, xx = x + kx - 1;
             if (yy < 0 || yy >= H || xx < 0 || xx >= Wd) continue;
-            const __nv_bfloat16* xp = X + (((size_t)b * H + yy) * Wd + xx) * Cin;
-            const __nv_bfloat16* wp = Wt + (size_t)co * 9 * Cin + (ky * 3 + kx) * Cin;
-            for (int c = 0; c < Cin; ++c) acc += __bfloat162float(xp[c]) * __bfloat162float(wp[c]);
+            const h16* xp = X + (((size_t)b * H + yy) * Wd + xx) * Cin;
+            const h16* wp = Wt + (size_t)co * 9 * Cin + (ky * 3 + kx) * Cin;
+            for (int c = 0; c < Cin; ++c) acc += dev_from_h16(xp[c]) * dev_from_h16(wp[c]);
         }
     if (bias) acc += bias[co];
     out[idx] = ref_act(acc, act);
@@ -116,11 +130,11 @@ static std::vector<float> fetch_f32(const float* d, size_t n) {
     CK(cudaMemcpy(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost));
     return h;
 }
-static std::vector<float> fetch_bf16(const __nv_bfloat16* d, size_t n) {
-    std::vector<__nv_bfloat16> h(n);
-    CK(cudaMemcpy(h.data(), d, n * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));
+static std::vector<float> fetch_bf16(const h16* d, size_t n) {
+    std::vector<h16> h(n);
+    CK(cudaMemcpy(h.data(), d, n * sizeof(h16), cudaMemcpyDeviceToHost));
     std::vector<float> f(n);
-    for (size_t i = 0; i < n; ++i) f[i] = __bfloat162float(h[i]);
+    for (size_t i = 0; i < n; ++i) f[i] = from_h16(h[i]);
     return f;
 }
 
@@ -144,8 +158,8 @@ static float bench(F&& f, int iters) {
 
 static void case_gemm(int M, int N, int K, int act, bool with_bias, bool with_res, int res_rows, bool out_f32,
                       bool with_head) {
-    __nv_bfloat16* A = dev_bf16((size_t)M * K, 1.0f);
-    __nv_bfloat16* W = dev_bf16((size_t)N * K, 1.0f / sqrtf((float)K));
+    h16* A = dev_bf16((size_t)M * K, 1.0f);
+    h16* W = dev_bf16((size_t)N * K, 1.0f / sqrtf((float)K));
     float* bias = with_bias ? dev_f32(N, 0.5f) : nullptr;
     float* res = with_res ? dev_f32((size_t)(res_rows > 0 ? res_rows : M) * N, 1.0f) : nullptr;
     float* hw = with_head ? dev_f32(N, 0.2f) : nullptr;
@@ -168,11 +182,11 @@ static void case_gemm(int M, int N, int K, int act, bool with_bias, bool with_re
     ep.residual = res;
     ep.res_rows = res_rows;
     ep.out = out;
-    ep.out_dtype = out_f32 ? SPG_F32 : SPG_BF16;
+    ep.out_dtype = out_f32 ? SPG_F32 : SPG_H16;
     ep.head_w = hw;
     ep.head_b = 0.25f;
     ep.head_out = head_out;
-    int rc = spg_linear_bf16(A, W, M, N, K, &ep, nullptr);
+    int rc = spg_linear_h16(A, W, M, N, K, &ep, nullptr);
     if (rc != SPG_OK) {
         printf("FAIL gemm M=%d N=%d K=%d: rc=%d %s\n", M, N, K, rc, spg_last_error());
         ++g_fail;
@@ -184,12 +198,12 @@ static void case_gemm(int M, int N, int K, int act, bool with_bias, bool with_re
         exit(100 + g_fail);
     }
     auto r = fetch_f32(ref, (size_t)M * N);
-    auto g = out_f32 ? fetch_f32((float*)out, (size_t)M * N) : fetch_bf16((__nv_bfloat16*)out, (size_t)M * N);
+    auto g = out_f32 ? fetch_f32((float*)out, (size_t)M * N) : fetch_bf16((h16*)out, (size_t)M * N);
     Stats s = compare(g, r, out_f32 ? 2e-3 : 2e-2, out_f32 ? 1e-3 : 1e-2);
     Stats sh;
     if (with_head) sh = compare(fetch_f32(head_out, M), fetch_f32(ref_h, M), 5e-3, 2e-3);
     float ms = 0;
-    if (g_perf) ms = bench([&] { spg_linear_bf16(A, W, M, N, K, &ep, nullptr); }, 10);
+    if (g_perf) ms = bench([&] { spg_linear_h16(A, W, M, N, K, &ep, nullptr); }, 10);
     const bool ok = s.bad == 0 && sh.bad == 0;
     printf("%s gemm M=%-6d N=%-5d K=%-5d act=%d bias=%d res=%d/%d f32=%d head=%d  max_abs=%.3e (ref max %.2f) head_err=%.3e",
            ok ? "PASS" : "FAIL", M, N, K, act, with_bias, with_res, res_rows, out_f32, with_head, s.max_abs, s.max_ref,
@@ -203,13 +217,13 @@ static void case_gemm(int M, int N, int K, int act, bool with_bias, bool with_re
 
 static void case_conv(int B, int H, int Wd, int Cin, int Cout, int act, bool with_head, bool store_out) {
     const size_t M = (size_t)B * H * Wd;
-    __nv_bfloat16* X = dev_bf16(M * Cin, 1.0f);
-    __nv_bfloat16* Wt = dev_bf16((size_t)Cout * 9 * Cin, 1.0f / sqrtf(9.0f * Cin));
+    h16* X = dev_bf16(M * Cin, 1.0f);
+    h16* Wt = dev_bf16((size_t)Cout * 9 * Cin, 1.0f / sqrtf(9.0f * Cin));
     float* bias = dev_f32(Cout, 0.5f);
     float* hw = with_head ? dev_f32(Cout, 0.2f) : nullptr;
     float *ref, *ref_h = nullptr, *head_out = nullptr;
     CK(cudaMalloc(&ref, M * Cout * 4));
-    __nv_bfloat16* out = nullptr;
+    h16* out = nullptr;
     if (store_out) {
         CK(cudaMalloc(&out, M * Cout * 2));
         CK(cudaMemset(out, 0xFF, M * Cout * 2));
@@ -226,11 +240,11 @@ static void case_conv(int B, int H, int Wd, int Cin, int Cout, int act, bool wit
     ep.bias = bias;
     ep.act = act;
     ep.out = out;
-    ep.out_dtype = SPG_BF16;
+    ep.out_dtype = SPG_H16;
     ep.head_w = hw;
     ep.head_b = -0.1f;
     ep.head_out = head_out;
-    int rc = spg_conv3x3_bf16(X, Wt, B, H, Wd, Cin, Cout, &ep, nullptr);
+    int rc = spg_conv3x3_h16(X, Wt, B, H, Wd, Cin, Cout, &ep, nullptr);
     if (rc != SPG_OK) {
         printf("FAIL conv B=%d H=%d W=%d Cin=%d Cout=%d: rc=%d %s\n", B, H, Wd, Cin, Cout, rc, spg_last_error());
         ++g_fail;
@@ -245,7 +259,7 @@ static void case_conv(int B, int H, int Wd, int Cin, int Cout, int act, bool wit
     if (store_out) s = compare(fetch_bf16(out, M * Cout), fetch_f32(ref, M * Cout), 2e-2, 1e-2);
     if (with_head) sh = compare(fetch_f32(head_out, M), fetch_f32(ref_h, M), 5e-3, 2e-3);
     float ms = 0;
-    if (g_perf) ms = bench([&] { spg_conv3x3_bf16(X, Wt, B, H, Wd, Cin, Cout, &ep, nullptr); }, 10);
+    if (g_perf) ms = bench([&] { spg_conv3x3_h16(X, Wt, B, H, Wd, Cin, Cout, &ep, nullptr); }, 10);
     const bool ok = s.bad == 0 && sh.bad == 0;
     printf("%s conv B=%d H=%-3d W=%-3d Cin=%-3d Cout=%-3d act=%d head=%d store=%d  max_abs=%.3e head_err=%.3e",
            ok ? "PASS" : "FAIL", B, H, Wd, Cin, Cout, act, with_head, store_out, s.max_abs, sh.max_abs);

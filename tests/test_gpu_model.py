@@ -1,0 +1,179 @@
+"""Whole-forward parity on a B200: the CUDA drop-in against (a) golden outputs of the REFERENCE class run
+verbatim (tests/golden/full_512.npz), (b) the fp32 CPU oracle on the same seeded weights / images, and
+(c) the reference's own scores (S-alpha, weighted F, E-phi, MAE) recomputed on both sets of masks.
+
+Bars (BASELINE.json north_star): masks within 1e-2 max-abs after sigmoid, scores within 1e-3.
+The fp16 build (default) is held to those bars; the bf16 build is measured and held to the looser
+bound its 7-bit mantissa allows (DESIGN.md "Numerics") so regressions still show.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = {"encoder": {"config_path": "configs/sam2.1/sam2.1_hiera_l.yaml",
+                   "checkpoint_path": "./checkpoints/sam2.1_hiera_large.pt", "variant": "large"}}
+MASK_TOL = 1e-2   # max-abs after sigmoid (north star)
+SCORE_TOL = 1e-3  # S-alpha / weighted-F / E-phi / MAE (north star)
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a B200")
+
+
+@pytest.fixture(scope="module")
+def model_fp16(spread_sd):
+    _need_gpu()
+    from spegnet_b200 import SPEGNet
+
+    m = SPEGNet(CFG, compute_dtype=torch.float16)
+    m.load_state_dict(spread_sd)
+    return m.to("cuda").eval()
+
+
+@pytest.fixture(scope="module")
+def model_bf16(spread_sd):
+    _need_gpu()
+    from spegnet_b200 import SPEGNet
+
+    m = SPEGNet(CFG, compute_dtype=torch.bfloat16)
+    m.load_state_dict(spread_sd)
+    return m.to("cuda").eval()
+
+
+def _images(n, size, seed=1):
+    return torch.randn(n, 3, size, size, generator=torch.Generator().manual_seed(seed))
+
+
+def _sig_err(a, b):
+    return float((a.float().cpu().sigmoid() - torch.as_tensor(b).float().sigmoid()).abs().max())
+
+
+def _ellipse_gt(n, size, seed=100):
+    """Seeded union of 1-3 random ellipses per image, binary {0,1}."""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.mgrid[0:size, 0:size]
+    out = []
+    for _ in range(n):
+        m = np.zeros((size, size), bool)
+        for _ in range(rng.randint(1, 4)):
+            cy, cx = rng.uniform(0.25, 0.75, 2) * size
+            ry, rx = rng.uniform(0.08, 0.3, 2) * size
+            m |= ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 <= 1.0
+        out.append(m.astype(np.float32))
+    return out
+
+
+def test_matches_reference_golden_512(model_fp16, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "full_512.npz"))
+    x = _images(1, 512, int(gold["input_seed"]))
+    with torch.inference_mode():
+        out = model_fp16(x.cuda())
+    preds = out["predictions"]
+    assert [tuple(p.shape) for p in preds] == [(1, 1, 128, 128), (1, 1, 256, 256), (1, 1, 512, 512)]
+    assert tuple(out["edge"].shape) == (1, 1, 64, 64)
+    assert all(p.dtype == torch.float32 for p in preds) and out["edge"].dtype == torch.float32
+    assert _sig_err(preds[0], gold["pred1"]) <= MASK_TOL
+    assert _sig_err(preds[1], gold["pred2"]) <= MASK_TOL
+    assert _sig_err(preds[2], gold["pred3"].astype(np.float32)) <= MASK_TOL + 1e-3  # golden pred3 is stored as fp16
+    assert _sig_err(out["edge"], gold["edge"]) <= MASK_TOL
+    # the call sites' post-processing works on the returned tensors (engine/predictor.py:367-368)
+    prob = preds[-1].sigmoid().squeeze().cpu().numpy()
+    assert prob.shape == (512, 512) and prob.dtype == np.float32
+    ctx = out["features"]["context"]
+    assert tuple(ctx.shape) == (1, 256, 64, 64) and ctx.dtype == torch.float32
+    assert set(out["features"].keys()) == {"context", "fused", "edge_features"}
+    np.testing.assert_allclose(ctx.mean(dim=(0, 2, 3)).cpu().numpy(), gold["context_mean"], atol=2e-2)
+
+
+@pytest.mark.parametrize("size,batch", [(512, 2), (256, 3)])
+def test_matches_oracle_masks_and_scores(model_fp16, spread_sd, size, batch):
+    from oracle import sod_metrics as M
+    from oracle.spegnet import spegnet_forward
+
+    x = _images(batch, size, seed=7 + size)
+    ref = spegnet_forward(spread_sd, x)
+    with torch.no_grad():
+        out = model_fp16(x.cuda())
+    for i in range(3):
+        assert _sig_err(out["predictions"][i], ref["predictions"][i]) <= MASK_TOL, f"pred{i + 1}"
+    assert _sig_err(out["edge"], ref["edge"]) <= MASK_TOL
+    for key in ("context", "fused", "edge_features"):
+        a, b = out["features"][key].cpu(), ref["features"][key]
+        assert float((a - b).abs().max()) <= 5e-3 * float(b.abs().max()) + 1e-2, key
+
+    # the judge's scores, through both of the reference's quantisation paths
+    gts = _ellipse_gt(batch, size)
+    ours, theirs = out["predictions"][-1].cpu(), ref["predictions"][-1]
+    for double_sigmoid in (False, True):  # trainer path (engine/trainer.py:416) / evaluator path (evaluator.py:544)
+        rows_a, rows_b = [], []
+        for i in range(batch):
+            gt_u8 = (gts[i] * 255).astype(np.uint8)
+            a, b = ours[i, 0].numpy(), theirs[i, 0].numpy()
+            if double_sigmoid:
+                a, b = 1 / (1 + np.exp(-a)), 1 / (1 + np.exp(-b))
+            rows_a.append(M.score_pair(M.quantise_like_reference(a), gt_u8))
+            rows_b.append(M.score_pair(M.quantise_like_reference(b), gt_u8))
+        agg_a, agg_b = M.aggregate(rows_a), M.aggregate(rows_b)
+        for k in ("s_alpha", "weighted_f", "e_phi", "mae", "mean_f"):
+            assert abs(agg_a[k] - agg_b[k]) <= SCORE_TOL, (k, double_sigmoid, agg_a[k], agg_b[k])
+
+
+def test_bf16_build_is_measured(model_bf16, spread_sd):
+    """bf16 storage (7-bit mantissa) cannot meet 1e-2 on spread logits; its error is pinned here so that it
+    neither regresses nor gets mistaken for the parity-grade build."""
+    from oracle.spegnet import spegnet_forward
+
+    x = _images(1, 256, seed=3)
+    ref = spegnet_forward(spread_sd, x)
+    with torch.no_grad():
+        out = model_bf16(x.cuda())
+    errs = [_sig_err(out["predictions"][i], ref["predictions"][i]) for i in range(3)]
+    assert max(errs) <= 8e-2, errs
+    assert max(errs) > MASK_TOL / 4  # sanity: this really is the lower-precision build
+
+
+def test_deterministic_and_caller_owned_outputs(model_fp16):
+    x = _images(2, 256, seed=11).cuda()
+    with torch.no_grad():
+        a = model_fp16(x)
+        a_pred = a["predictions"][-1].clone()
+        b = model_fp16(x * 0.5)  # a second forward must not overwrite the first call's outputs
+        c = model_fp16(x)
+    assert torch.equal(a["predictions"][-1], a_pred)
+    assert not torch.equal(b["predictions"][-1], a_pred)
+    for i in range(3):
+        assert torch.equal(a["predictions"][i], c["predictions"][i])  # bit-exact repeatability
+    assert torch.equal(a["edge"], c["edge"])
+    assert torch.equal(a["features"]["fused"], c["features"]["fused"])
+
+
+def test_batch_invariance_at_full_batch(model_fp16):
+    """Size-independent property at BASELINE's full configuration (B=64, S=512): every image's masks are
+    bit-identical to the ones it gets in a batch of one (tiles never straddle images, no cross-image op)."""
+    B = 64
+    x = _images(B, 512, seed=21).cuda()
+    with torch.no_grad():
+        full = model_fp16(x)
+        p3 = full["predictions"][-1]
+        e = full["edge"]
+        assert bool(torch.isfinite(p3).all())
+        assert float(p3.std()) > 1.0  # the fixture is not vacuous
+        for i in (0, 37, 63):
+            single = model_fp16(x[i:i + 1])
+            assert torch.equal(single["predictions"][-1][0], p3[i]), i
+            assert torch.equal(single["edge"][0], e[i]), i
+
+
+def test_launches_are_counted_and_native(model_fp16):
+    from spegnet_b200 import _lib
+
+    _lib.reset_launch_count()
+    with torch.no_grad():
+        model_fp16(_images(1, 256).cuda())
+    torch.cuda.synchronize()
+    assert _lib.launch_count() >= 350  # 48 blocks x 7-9 kernels + head, all from libspegnet_b200_fp16.so

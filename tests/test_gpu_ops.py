@@ -1,0 +1,259 @@
+"""Per-kernel parity: every C-ABI entry point against the plain fp32 PyTorch op it replaces, on a B200.
+Inputs are rounded to bf16 first where the kernel takes bf16, so the tolerance only has to absorb
+the output rounding (bf16 outputs: ~2^-8 relative) and fp32 summation order."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# Every test runs against both library variants (libspegnet_b200_fp16.so / _bf16.so).  Tolerances are
+# written for bf16 (2^-8 relative output rounding); fp16 is 8x tighter and must pass them a fortiori.
+H16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module", params=["fp16", "bf16"])
+def ops(request):
+    global H16
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from spegnet_b200 import _lib, ops as _ops
+
+    lib = _lib.load(request.param)
+    assert lib.spg_device_check() == 0, lib.spg_last_error()
+    H16 = torch.float16 if request.param == "fp16" else torch.bfloat16
+    return _ops
+
+
+def _bf(t):
+    return t.to(H16)
+
+
+def _close(got, ref, atol, rtol):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    assert bool((err <= tol).all()), f"max err {err.max().item():.4e} (ref max {ref.abs().max().item():.3f})"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (384, 144, 144), (512, 864, 288), (300, 192, 128), (1024, 576, 2304),
+                                   (1024, 512, 1152)])
+def test_linear_plain(ops, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda", dtype=H16)
+    ops.linear(a, w, out, bias=bias)
+    _close(out, a.float() @ w.float().t() + bias, 2e-2, 1e-2)
+
+
+def test_linear_gelu_residual_f32(ops):
+    M, N, K = 1024, 576, 576
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    ref = F.gelu(a.float() @ w.float().t() + bias) + res
+    out = res.clone()
+    ops.linear(a, w, out, bias=bias, act=ops.ACT_GELU, residual=out)  # in place, as the trunk uses it
+    _close(out, ref, 2e-4, 1e-4)
+
+
+def test_linear_broadcast_residual_and_head(ops):
+    M, N, K = 1024, 144, 160
+    g = torch.Generator(device="cuda").manual_seed(4)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    pos = torch.randn(256, N, device="cuda", generator=g)
+    out = torch.empty(M, N, device="cuda")
+    ops.linear(a, w, out, residual=pos, res_rows=256)
+    _close(out, a.float() @ w.float().t() + pos.repeat(4, 1), 2e-4, 1e-4)
+    hw = torch.randn(N, device="cuda", generator=g)
+    head = torch.empty(M, device="cuda")
+    ops.linear(a, w, None, act=ops.ACT_RELU, head_w=hw, head_b=0.5, head_out=head)
+    _close(head, F.relu(a.float() @ w.float().t()) @ hw + 0.5, 5e-4, 1e-4)
+
+
+def test_linear_rejects_bad_shapes(ops):
+    a = torch.zeros(128, 60, device="cuda", dtype=H16)
+    w = torch.zeros(64, 60, device="cuda", dtype=H16)
+    with pytest.raises(ValueError):
+        ops.linear(a, w, torch.empty(128, 64, device="cuda", dtype=H16))
+    with pytest.raises(ValueError):
+        ops.linear(a.float(), w, torch.empty(128, 64, device="cuda", dtype=H16))
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,head", [(2, 16, 64, 64, False), (1, 64, 256, 64, True), (1, 128, 320, 256, True),
+                                               (1, 256, 128, 128, False)])
+def test_conv3x3(ops, B, H, Cin, Cout, head):
+    g = torch.Generator(device="cuda").manual_seed(H + Cin)
+    x = _bf(torch.randn(B, H, H, Cin, device="cuda", generator=g))
+    w4 = _bf(torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Cin))
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    wk = w4.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = torch.empty(B * H * H, Cout, device="cuda", dtype=H16)
+    hw = torch.randn(Cout, device="cuda", generator=g) if head else None
+    ho = torch.empty(B, 1, H, H, device="cuda") if head else None
+    ops.conv3x3(x, wk, out, bias=bias, act=ops.ACT_RELU, head_w=hw, head_b=-0.25, head_out=ho)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), bias, padding=1))
+    _close(out.view(B, H, H, Cout).permute(0, 3, 1, 2), ref, 2e-2, 1e-2)
+    if head:
+        _close(ho, (ref * hw.view(1, -1, 1, 1)).sum(1, keepdim=True) - 0.25, 5e-3, 1e-3)
+
+
+@pytest.mark.parametrize("C", [144, 288, 576, 1152])
+def test_layernorm(ops, C):
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = torch.randn(1000, C, device="cuda", generator=g) * 3 + 1
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g)
+    y = torch.empty(1000, C, device="cuda", dtype=H16)
+    ops.layernorm(x, gamma, beta, y, 1e-6)
+    _close(y, F.layer_norm(x, (C,), gamma, beta, 1e-6), 2e-2, 1e-2)
+
+
+def test_patch_embed(ops):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, S = 2, 64
+    x = torch.randn(B, 3, S, S, device="cuda", generator=g)
+    w = torch.randn(144, 3, 7, 7, device="cuda", generator=g) / math.sqrt(147)
+    bias = torch.randn(144, device="cuda", generator=g)
+    cols = torch.empty(B * 256, 160, device="cuda", dtype=H16)
+    ops.patchify(x, cols)
+    wk = F.pad(w.reshape(144, 147), (0, 13)).to(H16).contiguous()
+    out = torch.empty(B * 256, 144, device="cuda")
+    ops.linear(cols, wk, out, bias=bias)
+    ref = F.conv2d(_bf(x).float(), _bf(w).float(), bias, stride=4, padding=3).permute(0, 2, 3, 1).reshape(-1, 144)
+    _close(out, ref, 1e-3, 1e-3)
+    assert float(cols[:, 147:].abs().max()) == 0.0
+
+
+def test_maxpool_and_cast(ops):
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(2, 16, 16, 288, device="cuda", generator=g)
+    y = torch.empty(2, 8, 8, 288, device="cuda")
+    ops.maxpool2x2(x, y, 2, 16, 16, 288)
+    assert torch.equal(y, F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
+    z = torch.empty(2 * 16 * 16 * 288, device="cuda", dtype=H16)
+    ops.cast_h16(x.view(-1), z)
+    assert torch.equal(z, x.view(-1).to(H16))
+
+
+def _ref_attention(qkv, B, H, D, heads, ws, qpool):
+    hd = D // heads
+    t = qkv.float().view(B, H, H, 3 * D)
+    ws = ws or H
+    t = t.view(B, H // ws, ws, H // ws, ws, 3 * D).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws, ws, 3, heads, hd)
+    q, k, v = t[:, :, :, 0], t[:, :, :, 1], t[:, :, :, 2]
+    wq = ws
+    if qpool:
+        q = F.max_pool2d(q.reshape(-1, ws, ws, D).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        wq = ws // 2
+        q = q.reshape(-1, wq, wq, heads, hd)
+    nw = q.shape[0]
+    q = q.reshape(nw, wq * wq, heads, hd).transpose(1, 2)
+    k = k.reshape(nw, ws * ws, heads, hd).transpose(1, 2)
+    v = v.reshape(nw, ws * ws, heads, hd).transpose(1, 2)
+    o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(nw, wq, wq, D)
+    Ho = H // 2 if qpool else H
+    o = o.view(B, H // ws, H // ws, wq, wq, D).permute(0, 1, 3, 2, 4, 5).reshape(B, Ho, Ho, D)
+    return o
+
+
+@pytest.mark.parametrize("H,heads,ws,qpool", [
+    (32, 2, 8, False),    # stage 1
+    (32, 4, 8, True),     # block 2: 16 pooled queries x 64 keys
+    (16, 4, 4, False),    # stage 2
+    (16, 8, 4, True),     # block 8: 4 pooled queries x 16 keys (CUDA-core path)
+    (32, 8, 16, False),   # stage 3 windows
+    (32, 8, 0, False),    # stage 3 global, 1024 keys (4 staged passes)
+    (32, 16, 16, True),   # block 44
+    (16, 16, 8, False),   # stage 4
+])
+def test_window_attention(ops, H, heads, ws, qpool):
+    B, D = 2, heads * 72
+    g = torch.Generator(device="cuda").manual_seed(H * 100 + heads + ws)
+    qkv = _bf(torch.randn(B * H * H, 3 * D, device="cuda", generator=g) * 1.5)
+    Ho = H // 2 if qpool else H
+    out = torch.full((B * Ho * Ho, D), float("nan"), device="cuda", dtype=H16)
+    ops.window_attention(qkv, out, B, H, H, D, heads, ws, qpool)
+    ref = _ref_attention(qkv, B, H, D, heads, ws, qpool)
+    _close(out.view(B, Ho, Ho, D), ref, 2e-2, 2e-2)
+
+
+def test_upsample_concat(ops):
+    g = torch.Generator(device="cuda").manual_seed(8)
+    a = _bf(torch.randn(2, 16, 16, 256, device="cuda", generator=g))
+    e = _bf(torch.randn(2, 8, 8, 64, device="cuda", generator=g))
+    out = torch.empty(2, 32, 32, 320, device="cuda", dtype=H16)
+    ops.upsample_concat(a, e, out)
+    up = lambda t: F.interpolate(t.float().permute(0, 3, 1, 2), size=(32, 32), mode="bilinear", align_corners=False)  # noqa: E731
+    ref = torch.cat([up(a), up(e)], 1).permute(0, 2, 3, 1)
+    _close(out, ref, 1e-2, 1e-2)
+    out2 = torch.empty(2, 32, 32, 256, device="cuda", dtype=H16)
+    ops.upsample_concat(a, None, out2)
+    _close(out2, up(a).permute(0, 2, 3, 1), 1e-2, 1e-2)
+
+
+def test_fusion_combine_se_scale(ops):
+    g = torch.Generator(device="cuda").manual_seed(9)
+    B, Hs, C = 2, 16, 512
+    g2 = torch.randn(B, Hs, Hs, C, device="cuda", generator=g)
+    g3 = torch.randn(B, Hs // 2, Hs // 2, C, device="cuda", generator=g)
+    g4 = torch.randn(B, Hs // 4, Hs // 4, C, device="cuda", generator=g)
+    bias = torch.randn(C, device="cuda", generator=g)
+    fused = torch.empty(B, Hs, Hs, C, device="cuda", dtype=H16)
+    rs = torch.empty(B, Hs, C, device="cuda")
+    ops.fusion_combine(g2, g3, g4, bias, fused, rs, B, Hs, C)
+    up = lambda t: F.interpolate(t.permute(0, 3, 1, 2), size=(Hs, Hs), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)  # noqa: E731
+    ref = F.relu(g2 + up(g3) + up(g4) + bias)
+    _close(fused, ref, 1e-2, 1e-2)
+    _close(rs, ref.sum(2), 1e-3, 1e-4)
+    w1 = torch.randn(32, C, device="cuda", generator=g) / math.sqrt(C)
+    w2 = torch.randn(C, 32, device="cuda", generator=g) / math.sqrt(32)
+    gate = torch.empty(B, C, device="cuda")
+    ops.pooled_mlp(rs, Hs, Hs * Hs, w1, None, 32, w2, gate, B, C)
+    ref_gate = torch.sigmoid(F.relu(ref.mean((1, 2)) @ w1.t()) @ w2.t())
+    _close(gate, ref_gate, 1e-5, 1e-4)
+    before = fused.clone()
+    ops.scale_channels(fused, gate, B, Hs * Hs, C)
+    _close(fused, before.float() * gate[:, None, None, :], 1e-2, 1e-2)
+
+
+def test_easpp(ops):
+    g = torch.Generator(device="cuda").manual_seed(10)
+    B, H = 2, 64
+    x = _bf(F.relu(torch.randn(B, H, H, 128, device="cuda", generator=g)))
+    rs = torch.empty(B, H, 128, device="cuda")
+    ops.row_sums(x, rs, B, H, H, 128)
+    _close(rs, x.float().sum(2), 1e-3, 1e-4)
+    wg = torch.randn(128, 128, device="cuda", generator=g) / math.sqrt(128)
+    bg = torch.randn(128, device="cuda", generator=g)
+    gvec = torch.empty(B, 128, device="cuda")
+    ops.pooled_mlp(rs, H, H * H, wg, bg, 128, None, gvec, B, 128)
+    ref_g = F.relu(x.float().mean((1, 2)) @ wg.t() + bg)
+    _close(gvec, ref_g, 1e-5, 1e-4)
+    dil = (1, 6, 12, 18)
+    dw = torch.randn(4, 128, 3, 3, device="cuda", generator=g) / 3
+    dwb = torch.randn(4, 128, device="cuda", generator=g)
+    wf = torch.randn(128, 5, device="cuda", generator=g) / math.sqrt(5)
+    wfb = torch.randn(128, device="cuda", generator=g)
+    y = torch.empty(B, H, H, 128, device="cuda", dtype=H16)
+    dw_k = dw.reshape(4, 128, 9).permute(0, 2, 1).contiguous()  # [4, tap, ch]
+    ops.easpp_branches(x, dw_k, dwb, ref_g.contiguous(), wf, wfb, y, B, H, H, dil)
+    xn = x.float().permute(0, 3, 1, 2)
+    br = [F.relu(F.conv2d(xn, dw[i].unsqueeze(1), dwb[i], padding=d, dilation=d, groups=128)) for i, d in enumerate(dil)]
+    br.append(ref_g[:, :, None, None].expand(-1, -1, H, H))
+    ref = F.relu(F.conv2d(torch.cat(br, 1), wf.view(128, 5, 1, 1), wfb, groups=128)).permute(0, 2, 3, 1)
+    _close(y, ref, 2e-2, 1e-2)
+
+
+def test_nhwc_to_nchw(ops):
+    x = _bf(torch.randn(2, 8, 8, 64, device="cuda"))
+    y = torch.empty(2, 64, 8, 8, device="cuda")
+    ops.nhwc_to_nchw_f32(x, y, 2, 64, 64)
+    assert torch.equal(y, x.float().permute(0, 3, 1, 2))

@@ -1,0 +1,114 @@
+"""CPU-side checks (no GPU): the C-ABI libraries load and export every symbol the header declares, the
+drop-in module mirrors the reference's constructor / state-dict / error contract, and the product never
+falls back to a CPU path."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = {"encoder": {"config_path": "configs/sam2.1/sam2.1_hiera_l.yaml",
+                   "checkpoint_path": "./checkpoints/sam2.1_hiera_large.pt", "variant": "large"},
+       "name": "spegnet", "image_processing": {"target_size": 512}}
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "spegnet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(spg_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.mark.parametrize("variant", ["fp16", "bf16"])
+def test_library_exports_every_declared_symbol(variant):
+    from spegnet_b200 import _lib
+
+    path = _lib.LIB_PATHS[variant]
+    assert os.path.exists(path), "run `python -m spegnet_b200.build` (or __graft_entry__.build()) first"
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/spegnet_b200.h but not exported by {path}"
+    # and the Python binding covers the same set
+    assert sorted(_lib.EXPORTS) == declared
+    loaded = _lib.load(variant)
+    assert loaded.spg_version() >= 100
+    assert bool(loaded.spg_half_is_fp16()) == (variant == "fp16")
+    assert loaded.spg_last_error() == b"" or isinstance(loaded.spg_last_error(), bytes)
+
+
+def test_argument_errors_surface_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it can be exercised on the build box."""
+    from spegnet_b200 import _lib
+
+    lib = _lib.load("fp16")
+    ep = _lib.Epilogue()
+    rc = lib.spg_linear_h16(None, None, 128, 64, 64, ctypes.byref(ep), None)
+    assert rc == -1 and b"NULL" in lib.spg_last_error()
+    rc = lib.spg_linear_h16(ctypes.c_void_p(16), ctypes.c_void_p(16), 128, 60, 64, ctypes.byref(ep), None)
+    assert rc == -1 and b"multiple of 16" in lib.spg_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc, "spg_linear_h16", "fp16")
+
+
+@pytest.fixture(scope="module")
+def model():
+    from spegnet_b200 import SPEGNet
+
+    return SPEGNet(CFG)
+
+
+def test_state_dict_schema_matches_reference(model, spread_sd):
+    """Key names and shapes are the reference's (models/spegnet.py:94-135 + sam2 trunk names), so a
+    reference checkpoint's ['model_state_dict'] loads with strict=True."""
+    ours = model.state_dict()
+    assert set(ours) == set(spread_sd)
+    for k, v in spread_sd.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), k
+    assert sum(p.numel() for p in model.parameters()) == 215_442_100
+    res = model.load_state_dict(spread_sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    # trainer-style parameter grouping by name still works (engine/trainer.py:284-294)
+    names = [n for n, _ in model.named_parameters()]
+    assert any("encoder" in n for n in names) and any("bn" in n for n in names) and any("norm" in n for n in names)
+
+
+def test_constructor_and_input_errors_match_reference(model):
+    from spegnet_b200 import SPEGNet
+
+    with pytest.raises(ValueError):  # models/feature_encoding.py:150-151
+        SPEGNet({"encoder": {"config_path": "", "checkpoint_path": "", "variant": "gigantic"}})
+    with pytest.raises(KeyError):
+        SPEGNet({})
+    with pytest.raises(ValueError, match="4D"):  # models/feature_encoding.py:230-231
+        model(torch.zeros(3, 512, 512))
+    with pytest.raises(ValueError, match="divisible by 32"):  # :232-233
+        model(torch.zeros(1, 3, 500, 500))
+    with pytest.raises(NotImplementedError):
+        model.train()
+
+
+def test_no_cpu_fallback(model):
+    """A CPU tensor must fail loudly instead of silently running an eager / oracle path."""
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, 3, 512, 512))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "spegnet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports oracle"
+
+
+def test_trunk_geometry_agrees_with_oracle():
+    from oracle.hiera import HieraConfig, block_specs
+    from spegnet_b200.schema import trunk_blocks
+
+    for a, b in zip(trunk_blocks(), block_specs(HieraConfig())):
+        assert (a.index, a.stage, a.dim_in, a.dim_out, a.heads, a.window, a.q_pool) == (
+            b.index, b.stage, b.dim_in, b.dim_out, b.heads, b.window, bool(b.q_stride))
