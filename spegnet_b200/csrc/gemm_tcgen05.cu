@@ -3,12 +3,13 @@
 //   D[M,N] = epilogue( A[M,K] * W[N,K]^T )        bf16 operands, fp32 accumulation in TMEM
 //
 // One CTA per SM loops over 128 x block_n output tiles (n fastest, so concurrently running CTAs
-// share A tiles through L2).  Roles (192 threads):
+// share A tiles through L2).  Roles (320 threads):
 //   warp 0      TMA producer   - fills a ring of {A 128x64, W block_n x 64} bf16 stages (128B swizzle)
 //   warp 1      MMA issuer     - one thread issues tcgen05.mma (M=128, N=block_n, K=16) x4 per stage,
 //                                tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2..5  epilogue       - tcgen05.ld the accumulator (thread == output row), bias / GELU /
-//                                ReLU / fp32 residual / fused N->1 head, vectorised stores
+//   warps 2..9  epilogue       - tcgen05.ld the accumulator (thread == output row, two warps per TMEM
+//                                lane quarter split the columns), bias / GELU / ReLU / fp32 residual /
+//                                fused N->1 head, vectorised stores
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 //
@@ -31,11 +32,12 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kTmemCols = 512;
 constexpr int kAccStageCols = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
+constexpr int kEpiScratch = (2 * 256 + 256 + 128) * 4;  // bias[2][256], head weights[256], head partials[128]
 
 struct GemmArgs {
     int M, N;
@@ -91,7 +93,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), 4);  // one arrive per epilogue warp
+            mbar_init(tmem_empty_bar(a), 8);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -180,45 +182,63 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+        // ===================== epilogue (warps 2..9) =====================
+        // Two warps per TMEM lane quarter: both own the same 32 output rows, each takes half of the
+        // tile's 16-column chunks.  Per tile: bias (and head weights) are staged in smem BEFORE the
+        // accumulator is awaited, TMEM loads are double-buffered against the arithmetic, and the fp32
+        // residual of the next chunk is prefetched, so no global / TMEM latency sits on the critical path.
+        const int ewarp = warp - 2;                // 0..7
+        const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+        const int half = ewarp >> 2;               // which half of the chunks
+        const int etid = threadIdx.x - 64;         // 0..255
         const int row_in_tile = quarter * 32 + lane;
+        const int chunks = p.block_n >> 4;
+        const int c_begin = half == 0 ? 0 : (chunks + 1) >> 1;
+        const int c_end = half == 0 ? (chunks + 1) >> 1 : chunks;
+        float* bias_s = reinterpret_cast<float*>(smem_raw + (tiles_addr - raw_addr) + p.stages * stage_bytes + 256);
+        float* headw_s = bias_s + 2 * 256;         // [2][256] bias, [256] head weights, [128] head partials
+        float* headp_s = headw_s + 256;
+        if (p.head_w != nullptr && etid < p.block_n) headw_s[etid] = __ldg(p.head_w + etid);  // num_n_tiles == 1
         int acc = 0;
         uint32_t acc_phase = 0;
+        int buf = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_blk = tile / p.num_n_tiles;
             const int n_blk = tile - m_blk * p.num_n_tiles;
-            mbar_wait(tmem_full_bar(acc), acc_phase);
-            tc_fence_after();
+            const int n0 = n_blk * p.block_n;
+            float* bs = bias_s + buf * 256;
+            if (etid < p.block_n) bs[etid] = p.bias != nullptr ? __ldg(p.bias + n0 + etid) : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const int row = m_blk * kBlockM + row_in_tile;
             const bool row_ok = row < p.M;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStageCols;
-            const size_t out_off = static_cast<size_t>(row) * p.N;
+            const size_t out_off = static_cast<size_t>(row) * p.N + n0;
             const float* res_row = nullptr;
-            if (p.residual != nullptr) {
+            if (p.residual != nullptr && row_ok) {
                 const int rr = p.res_rows > 0 ? (row % p.res_rows) : row;
-                res_row = p.residual + static_cast<size_t>(rr) * p.N;
+                res_row = p.residual + static_cast<size_t>(rr) * p.N + n0;
             }
+            float4 rnext[4];
+            if (res_row != nullptr) {
+                const float4* r4 = reinterpret_cast<const float4*>(res_row + c_begin * 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rnext[i] = r4[i];
+            }
+            mbar_wait(tmem_full_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStageCols;
             float head_acc = 0.f;
-            const int chunks = p.block_n >> 4;
-            for (int c = 0; c < chunks; ++c) {
-                uint32_t raw[16];
-                tmem_ld16(taddr + c * 16, raw);
-                tmem_ld_wait();
-                const int col0 = n_blk * p.block_n + c * 16;
+
+            auto process = [&](const uint32_t (&raw)[16], int c) {
+                const int col = c * 16;  // column inside the tile
                 float v[16];
+                const float4* b4 = reinterpret_cast<const float4*>(bs + col);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-                if (p.bias != nullptr) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b = __ldg(b4 + i);
-                        v[4 * i + 0] += b.x;
-                        v[4 * i + 1] += b.y;
-                        v[4 * i + 2] += b.z;
-                        v[4 * i + 3] += b.w;
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b = b4[i];
+                    v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x;
+                    v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
+                    v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
+                    v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
                 }
                 if (p.act == SPG_ACT_RELU) {
 #pragma unroll
@@ -227,22 +247,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
                 }
-                if (res_row != nullptr && row_ok) {
-                    const float4* r4 = reinterpret_cast<const float4*>(res_row + col0);
+                if (res_row != nullptr) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 r = r4[i];
-                        v[4 * i + 0] += r.x;
-                        v[4 * i + 1] += r.y;
-                        v[4 * i + 2] += r.z;
-                        v[4 * i + 3] += r.w;
+                        v[4 * i + 0] += rnext[i].x;
+                        v[4 * i + 1] += rnext[i].y;
+                        v[4 * i + 2] += rnext[i].z;
+                        v[4 * i + 3] += rnext[i].w;
+                    }
+                    if (c + 1 < c_end) {  // prefetch the next chunk's residual
+                        const float4* r4 = reinterpret_cast<const float4*>(res_row + col + 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) rnext[i] = r4[i];
                     }
                 }
                 if (p.head_w != nullptr) {
-                    const float4* w4 = reinterpret_cast<const float4*>(p.head_w + col0);
+                    const float4* w4 = reinterpret_cast<const float4*>(headw_s + col);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 w = __ldg(w4 + i);
+                        const float4 w = w4[i];
                         head_acc = fmaf(v[4 * i + 0], w.x, head_acc);
                         head_acc = fmaf(v[4 * i + 1], w.y, head_acc);
                         head_acc = fmaf(v[4 * i + 2], w.z, head_acc);
@@ -251,26 +274,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
                 if (p.out != nullptr && row_ok) {
                     if (p.out_f32) {
-                        float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + col0);
+                        float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + col);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     } else {
-                        uint4* o4 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + out_off + col0);
+                        uint4* o4 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + out_off + col);
                         o4[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
                                            pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                         o4[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
                                            pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                     }
                 }
+            };
+
+            uint32_t ra[16], rb[16];
+            if (c_begin < c_end) tmem_ld16(taddr + c_begin * 16, ra);
+            for (int c = c_begin; c < c_end; c += 2) {
+                tmem_ld_wait();
+                if (c + 1 < c_end) tmem_ld16(taddr + (c + 1) * 16, rb);
+                process(ra, c);
+                if (c + 1 < c_end) {
+                    tmem_ld_wait();
+                    if (c + 2 < c_end) tmem_ld16(taddr + (c + 2) * 16, ra);
+                    process(rb, c + 1);
+                }
             }
-            if (p.head_w != nullptr && row_ok) p.head_out[row] = head_acc + p.head_b;
             // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (p.head_w != nullptr) {
+                // combine the two column halves of the fused N->1 head through smem
+                if (half == 1) headp_s[row_in_tile] = head_acc;
+                asm volatile("bar.sync 2, 256;" ::: "memory");
+                if (half == 0 && row_ok) p.head_out[row] = head_acc + headp_s[row_in_tile] + p.head_b;
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
+            buf ^= 1;
         }
     }
 
@@ -287,12 +329,12 @@ int pick_block_n(int N) {
 
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, cudaStream_t stream) {
     const int stage_bytes = kAStageBytes + a.block_n * 128;
-    int stages = (kSmemBudget - 1024 - 256) / stage_bytes;
+    int stages = (kSmemBudget - 1024 - 256 - kEpiScratch) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > a.num_k_chunks + 1) stages = a.num_k_chunks + 1;  // no point in a deeper ring
     if (stages < 2) stages = 2;
     a.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 256;
+    const int smem = stages * stage_bytes + 1024 + 256 + kEpiScratch;
     static bool attr_set = false;
     if (!attr_set) {
         SPG_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel,
