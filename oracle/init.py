@@ -20,9 +20,12 @@ from .hiera import HieraConfig, block_specs
 # multipliers on the 1x1 prediction / edge heads, calibrated once so that the logit std is ~2
 HEAD_GAIN = {"decoder.pred_heads.0": 4.8, "decoder.pred_heads.1": 3.84, "decoder.pred_heads.2": 2.8,
              "edge_detector.edge_conv": 3.84}
-# ... and biases that re-centre the logits (post-ReLU channel means shift them by several units)
-HEAD_BIAS = {"decoder.pred_heads.0.bias": -0.75, "decoder.pred_heads.1.bias": 9.68,
-             "decoder.pred_heads.2.bias": -10.08, "edge_detector.edge_conv.bias": 8.24}
+# ... and biases that re-centre the logits (post-ReLU channel means shift them by several units) and then
+# move the mask logits to a mean of about -1.6: ~25 % foreground, like a camouflaged object in a scene.  With
+# >= 50 % foreground the reference's adaptive E-phi threshold min(2*mean, 1) saturates at 1.0 and the score
+# depends on the few pixels quantised to the top grey level -- a degenerate regime for a parity check.
+HEAD_BIAS = {"decoder.pred_heads.0.bias": -2.35, "decoder.pred_heads.1.bias": 8.08,
+             "decoder.pred_heads.2.bias": -11.68, "edge_detector.edge_conv.bias": 8.24}
 
 
 def _gen(seed: int, key: str) -> torch.Generator:

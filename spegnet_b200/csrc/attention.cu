@@ -5,13 +5,16 @@
 // addressing here: tokens are gathered straight out of the fused qkv GEMM output [tokens, 3*D] and
 // the context is scattered to its final token position, nothing is permuted or copied in HBM.
 //
-// Round-1 implementation: warp-level mma.sync (m16n8k16 bf16, fp32 accumulate) with K / V of the
-// window staged once per CTA in shared memory by cp.async, online softmax in registers.  Attention is
-// 4.7 % of the model's FLOPs; moving it to tcgen05 is listed as next work in DESIGN.md.
+// Round-1 implementation: warp-level mma.sync (m16n8k16, fp32 accumulate) with the window's K / V tiles
+// brought into shared memory by TMA -- a window is one box {72 ch, ws, ws, 1} of the qkv tensor viewed as
+// [B, H, W, 3D], so the "window partition" costs one descriptor-driven copy and no address arithmetic --
+// and the online softmax in registers.  Attention is 4.7 % of the model's FLOPs;
+// moving the two GEMMs of it to tcgen05 is listed as next work in DESIGN.md.
 #include <atomic>
 
 #include "common.h"
 #include "half16.cuh"
+#include "ptx.cuh"
 
 namespace spg {
 extern std::atomic<long long> g_launches;
@@ -31,6 +34,7 @@ struct AttnParams {
     int Nk, Nq;  // keys / queries per window
     int wpc;     // windows per CTA (Nq < 64) else 1
     int qtiles;  // 64-row query tiles per window (Nq >= 64) else 1
+    int box_h;   // window rows per K/V TMA box (box = 72 ch x ws x box_h tokens, <= 256 tokens)
     float scale_log2e;
 };
 
@@ -69,12 +73,19 @@ __device__ __forceinline__ long long window_token(const AttnParams& p, int b, in
 }
 
 template <int KB>  // keys consumed per softmax step (16 or 64)
-__global__ void __launch_bounds__(kThreads) window_attention_kernel(const AttnParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    h16* Ks = reinterpret_cast<h16*>(smem);
-    h16* Vs = Ks + kRowsSmem * kHd + 8;
-    const uint32_t Ks_u = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
-    const uint32_t Vs_u = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
+__global__ void __launch_bounds__(kThreads)
+window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t kv_bar;
+    const uint32_t Ks_u = (smem_u32(smem) + 127u) & ~127u;  // TMA destinations: 128-byte aligned
+    const uint32_t Vs_u = Ks_u + kRowsSmem * kHd * 2;
+    const uint32_t bar_u = smem_u32(&kv_bar);
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_kv);
+        mbar_init(bar_u, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -142,26 +153,22 @@ __global__ void __launch_bounds__(kThreads) window_attention_kernel(const AttnPa
     for (int kbase = 0; kbase < rows_total; kbase += kRowsSmem) {
         const int rows = min(kRowsSmem, rows_total - kbase);
         if (kbase > 0) __syncthreads();  // everyone is done with the previous K/V pass
-        // ---- stage K and V rows: 9 x 16 B per row each
-        for (int idx = threadIdx.x; idx < rows * 18; idx += kThreads) {
-            const int r = idx / 18, j = idx - r * 18;
-            const int rr = kbase + r;  // CTA-level key row
-            int kw = win0, kl = rr;
-            if (p.wpc > 1) {
-                kw = win0 + rr / p.Nk;
-                kl = rr - (rr / p.Nk) * p.Nk;
+        // ---- stage K and V rows with TMA: one box per (window, K|V); a pass covers box_h window rows
+        if (threadIdx.x == 0) {
+            const int nbox = p.wpc > 1 ? p.wpc : 1;
+            mbar_arrive_expect_tx(bar_u, static_cast<uint32_t>(rows) * kHd * 2u * 2u);
+            for (int w = 0; w < nbox; ++w) {
+                const int kw = win0 + w;
+                const int kb = kw / wins_per_img;
+                const int kwr = kw - kb * wins_per_img;
+                const int kwy = kwr / p.nwx, kwx = kwr - kwy * p.nwx;
+                const int y = kwy * p.ws + (p.wpc > 1 ? 0 : (kbase / p.ws));
+                const uint32_t dst_off = static_cast<uint32_t>(w) * p.Nk * kHd * 2u;
+                tma_load_4d(Ks_u + dst_off, &tmap_kv, bar_u, p.D + head * kHd, kwx * p.ws, y, kb);
+                tma_load_4d(Vs_u + dst_off, &tmap_kv, bar_u, 2 * p.D + head * kHd, kwx * p.ws, y, kb);
             }
-            const int kb_ = kw / wins_per_img;
-            const int kwr = kw - kb_ * wins_per_img;
-            const long long tok = window_token(p, kb_, kwr / p.nwx, kwr % p.nwx, kl);
-            const bool isv = j >= 9;
-            const int jj = isv ? j - 9 : j;
-            const h16* src = p.qkv + tok * ld + (isv ? 2 : 1) * p.D + head * kHd + jj * 8;
-            const uint32_t dst = (isv ? Vs_u : Ks_u) + (r * kHd + jj * 8) * 2;
-            cp_async16(dst, src);
         }
-        cp_async_wait_all();
-        __syncthreads();
+        mbar_wait(bar_u, static_cast<uint32_t>(kbase / kRowsSmem) & 1u);
 
         // ---- this warp's slice of the staged rows
         int kbeg = 0, kend = rows;
@@ -360,7 +367,7 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // tensor-core path: 64-row query tiles over <=256-key passes, or four 16-query windows per CTA
     const bool big = p.Nq % 64 == 0 && p.Nk % 64 == 0 && (p.Nk <= kRowsSmem || p.Nk % kRowsSmem == 0);
-    const bool quad = p.Nq == 16 && (p.Nk == 16 || p.Nk == 64) && nwin % 4 == 0;
+    const bool quad = (p.Nq == 16 || p.Nq == 4) && (p.Nk == 16 || p.Nk == 64) && nwin % 4 == 0;
     const bool mma_ok = big || quad;
     if (!mma_ok) {
         const long long warps = static_cast<long long>(nwin) * heads * p.Nq;
@@ -369,9 +376,13 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
         SPG_CHECK_LAUNCH();
         return SPG_OK;
     }
-    p.wpc = p.Nq < 64 ? 64 / p.Nq : 1;
+    p.wpc = p.Nq < 64 ? 4 : 1;  // one window per warp; rows >= Nq of a warp's 16-row tile are masked off
     p.qtiles = p.Nq >= 64 ? p.Nq / 64 : 1;
-    const int smem = (2 * kRowsSmem * kHd + 16) * 2;
+    p.box_h = p.Nk <= kRowsSmem ? ws : kRowsSmem / ws;
+    SPG_CHECK_ARG(ws <= 256 && p.box_h >= 1 && ws * p.box_h <= kRowsSmem, "window %d too wide for the K/V staging", ws);
+    CUtensorMap tmap;
+    if (int rc = make_tmap_qkv_window(&tmap, qkv, B, H, W, 3 * D, kHd, ws, p.box_h)) return rc;
+    const int smem = 2 * kRowsSmem * kHd * 2 + 128;
     static bool attr_set = false;
     if (!attr_set) {
         SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -380,9 +391,9 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     }
     dim3 grid(p.wpc > 1 ? nwin / p.wpc : nwin * p.qtiles, heads);
     if (p.Nk == 16)
-        window_attention_kernel<16><<<grid, kThreads, smem, st>>>(p);
+        window_attention_kernel<16><<<grid, kThreads, smem, st>>>(tmap, p);
     else
-        window_attention_kernel<64><<<grid, kThreads, smem, st>>>(p);
+        window_attention_kernel<64><<<grid, kThreads, smem, st>>>(tmap, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;

@@ -58,13 +58,17 @@ EncodeTiledFn encode_fn() {
 }
 
 int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims,
-           const cuuint64_t* strides, const cuuint32_t* box) {
+           const cuuint64_t* strides, const cuuint32_t* box,
+           int dtype = -1 /* -1: the library's 16-bit type, 1: fp32 */,
+           CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(SPG_ERR_INVALID, "TMA operand must be 16-byte aligned");
     cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(out, (kHalfIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), rank, const_cast<void*>(base), dims, strides, box,
-                    elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : (kHalfIsFp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+    CUresult r = fn(out, dt, rank, const_cast<void*>(base), dims, strides, box,
+                    elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return SPG_OK;
@@ -82,6 +86,20 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
     return encode(out, base, 2, dims, strides, box);
 }
 
+int make_tmap_epilogue(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, int elem_is_f32,
+                       uint32_t box_cols) {
+    const uint64_t esize = elem_is_f32 ? 4 : 2;
+    const uint64_t row_bytes = box_cols * esize;
+    if (row_bytes != 32 && row_bytes != 64 && row_bytes != 128) return fail(SPG_ERR_INVALID, "bad epilogue box");
+    if ((cols * esize) % 16 != 0) return fail(SPG_ERR_INVALID, "epilogue row pitch must be a multiple of 16 bytes");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * esize};
+    cuuint32_t box[2] = {box_cols, 32};
+    return encode(out, base, 2, dims, strides, box, elem_is_f32 ? 1 : -1,
+                  row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
+}
+
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
                    uint32_t box_h, uint32_t box_w) {
     if ((C * 2) % 16 != 0) return fail(SPG_ERR_INVALID, "channel pitch must be a multiple of 16 bytes");
@@ -89,6 +107,16 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
     cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
     cuuint32_t box[4] = {64, box_w, box_h, 1};
     return encode(out, base, 4, dims, strides, box);
+}
+
+int make_tmap_qkv_window(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t ld,
+                         uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+    if ((ld * 2) % 16 != 0 || (box_c * 2) % 16 != 0) return fail(SPG_ERR_INVALID, "qkv row pitch / box must be multiples of 16 bytes");
+    if (box_w > 256 || box_h > 256 || box_c > 256) return fail(SPG_ERR_INVALID, "qkv window box too large");
+    cuuint64_t dims[4] = {ld, W, H, B};
+    cuuint64_t strides[3] = {ld * 2, W * ld * 2, H * W * ld * 2};
+    cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+    return encode(out, base, 4, dims, strides, box, -1, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 }  // namespace spg

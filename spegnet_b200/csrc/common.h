@@ -40,6 +40,17 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
                    uint32_t box_h, uint32_t box_w);
 
+// [rows, cols] row-major epilogue tile map (output store / fp32 residual load): box = 32 rows x box_cols
+// columns (16 or 32); the swizzle mode equals the box row size (32 / 64 / 128 bytes), which makes the
+// row-per-thread staging accesses conflict free.
+int make_tmap_epilogue(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, int elem_is_f32,
+                       uint32_t box_cols);
+
+// qkv [B*H*W, ld] viewed as [B, H, W, ld]: box = {box_c channels, box_w, box_h, 1 image}, no swizzle
+// (dense rows of box_c elements in shared memory).  One box = the K or V tile of one attention window / head.
+int make_tmap_qkv_window(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t ld,
+                         uint32_t box_c, uint32_t box_w, uint32_t box_h);
+
 int sm_count();
 
 }  // namespace spg

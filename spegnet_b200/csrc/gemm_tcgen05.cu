@@ -1,15 +1,19 @@
 // Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
 //
-//   D[M,N] = epilogue( A[M,K] * W[N,K]^T )        bf16 operands, fp32 accumulation in TMEM
+//   D[M,N] = epilogue( A[M,K] * W[N,K]^T )        16-bit operands (fp16 / bf16), fp32 accumulation in TMEM
 //
 // One CTA per SM loops over 128 x block_n output tiles (n fastest, so concurrently running CTAs
 // share A tiles through L2).  Roles (320 threads):
-//   warp 0      TMA producer   - fills a ring of {A 128x64, W block_n x 64} bf16 stages (128B swizzle)
+//   warp 0      TMA producer   - fills a ring of {A 128x64, W block_n x 64} stages (128B swizzle)
 //   warp 1      MMA issuer     - one thread issues tcgen05.mma (M=128, N=block_n, K=16) x4 per stage,
 //                                tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2..9  epilogue       - tcgen05.ld the accumulator (thread == output row, two warps per TMEM
-//                                lane quarter split the columns), bias / GELU / ReLU / fp32 residual /
-//                                fused N->1 head, vectorised stores
+//   warps 2..9  epilogue       - two warps per TMEM lane quarter split the tile's 16-column chunks;
+//                                thread == output row.  Per chunk: tcgen05.ld (double-buffered) -> bias
+//                                (staged in smem per tile) -> GELU / ReLU -> fp32 residual -> fused N->1
+//                                head -> swizzled smem staging -> TMA store.  The fp32 residual chunk is
+//                                TMA-loaded into the same staging buffer two chunks ahead, so neither
+//                                the residual read nor the output write touches the LSU with a
+//                                row-per-thread (32 cache lines per instruction) access pattern.
 // The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 //
@@ -17,6 +21,7 @@
 // {64 ch, tile_w, tile_h, 1 image} of the NHWC input at (x0+dx-1, y0+dy-1); the zero halo comes
 // from TMA out-of-bounds fill, so the same MMA / epilogue pipeline serves both modes.
 #include <atomic>
+#include <cstring>
 
 #include "common.h"
 #include "half16.cuh"
@@ -33,11 +38,14 @@ constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kEpiWarps = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStageCols = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kEpiScratch = (2 * 256 + 256 + 128) * 4;  // bias[2][256], head weights[256], head partials[128]
+constexpr int kBarBytes = 512;                                 // pipeline barriers + residual barriers
+constexpr int kEpiScratch = (2 * 256 + 256 + 128) * 4;          // bias[2][256], head weights[256], head partials[128]
+constexpr int kResSlots = 3;                                    // staging ring depth when a residual is streamed in
 
 struct GemmArgs {
     int M, N;
@@ -50,24 +58,44 @@ struct GemmArgs {
     // epilogue
     const float* bias;
     int act;
-    const float* residual;
+    int has_res;
     int res_rows;
-    void* out;
+    int has_out;
     int out_f32;
+    int nslots;       // staging ring depth per epilogue warp (kResSlots)
+    int group;        // 16-column chunks per staging buffer / TMA op (1 or 2)
+    int row_bytes;    // bytes per staging row = group * 16 * sizeof(out)   (32 / 64 / 128)
+    int buf_bytes;    // 32 * row_bytes
+    int piece_shift, piece_mask;  // swizzle of the 16-byte pieces of a staging row
     const float* head_w;
     float head_b;
     float* head_out;
 };
 
+// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with a single-branch erf:
+//   erf(t) = 1 - 2^(t q(t)),  q = degree-5 minimax fit of log2(erfc(t)) / t on [0, 4],  t = min(|z|, 4)
+// max |erf error| 3.1e-7, max |GELU error| 4.8e-7 over all x when evaluated in fp32 (fit + check:
+// DESIGN.md "Numerics"); libdevice erff costs ~4x the issue slots because both of its branches are predicated.
 __device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    const float z = x * 0.70710678118654752440f;
+    const float t = fminf(fabsf(z), 4.0f);
+    float q = 0.00014203718455974013f;
+    q = fmaf(q, t, -0.0036641715560108423f);
+    q = fmaf(q, t, 0.03089582547545433f);
+    q = fmaf(q, t, -0.14969903230667114f);
+    q = fmaf(q, t, -0.9181656241416931f);
+    q = fmaf(q, t, -1.6279250383377075f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * q));
+    const float erf_z = copysignf(1.0f - e, z);
+    const float hx = 0.5f * x;
+    return fmaf(hx, erf_z, hx);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) { return pack2(lo, hi); }
-
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                    const __grid_constant__ CUtensorMap tmap_b, const GemmArgs p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                    const GemmArgs p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -79,6 +107,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     auto tmem_full_bar = [&](int a) { return bar_addr + 8u * (2 * p.stages + a); };
     auto tmem_empty_bar = [&](int a) { return bar_addr + 8u * (2 * p.stages + 2 + a); };
     const uint32_t tmem_slot = bar_addr + 8u * (2 * p.stages + 4);
+    auto res_bar = [&](int ew, int slot) { return bar_addr + 256u + 8u * (ew * kResSlots + slot); };
+    const uint32_t scratch_addr = bar_addr + kBarBytes;
+    const uint32_t staging_addr = (scratch_addr + kEpiScratch + 1023u) & ~1023u;  // 128B-swizzle atoms: 1 KB aligned
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -87,14 +118,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
+        if (p.has_out) tma_prefetch_desc(&tmap_out);
+        if (p.has_res) tma_prefetch_desc(&tmap_res);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), 8);  // one arrive per epilogue warp
+            mbar_init(tmem_empty_bar(a), kEpiWarps);  // one arrive per epilogue warp
         }
+        for (int ew = 0; ew < kEpiWarps; ++ew)
+            for (int s = 0; s < kResSlots; ++s) mbar_init(res_bar(ew, s), 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -166,7 +201,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kAStageBytes);
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance 32 B (= 16 bf16) along K inside the 128 B swizzle atom
+                        // advance 32 B (= 16 elements) along K inside the 128 B swizzle atom
                         const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
                         umma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (kc | k) != 0);
                     }
@@ -183,53 +218,76 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
-        // Two warps per TMEM lane quarter: both own the same 32 output rows, each takes half of the
-        // tile's 16-column chunks.  Per tile: bias (and head weights) are staged in smem BEFORE the
-        // accumulator is awaited, TMEM loads are double-buffered against the arithmetic, and the fp32
-        // residual of the next chunk is prefetched, so no global / TMEM latency sits on the critical path.
-        const int ewarp = warp - 2;                // 0..7
-        const int quarter = warp & 3;              // TMEM lane quarter this warp may access
-        const int half = ewarp >> 2;               // which half of the chunks
-        const int etid = threadIdx.x - 64;         // 0..255
+        const int ewarp = warp - 2;      // 0..7
+        const int quarter = warp & 3;    // TMEM lane quarter this warp may access
+        const int half = ewarp >> 2;     // which half of the chunks
+        const int etid = threadIdx.x - 64;
         const int row_in_tile = quarter * 32 + lane;
         const int chunks = p.block_n >> 4;
         const int c_begin = half == 0 ? 0 : (chunks + 1) >> 1;
         const int c_end = half == 0 ? (chunks + 1) >> 1 : chunks;
-        float* bias_s = reinterpret_cast<float*>(smem_raw + (tiles_addr - raw_addr) + p.stages * stage_bytes + 256);
-        float* headw_s = bias_s + 2 * 256;         // [2][256] bias, [256] head weights, [128] head partials
+        const int n_my = c_end - c_begin;
+        float* bias_s = reinterpret_cast<float*>(smem_raw + (scratch_addr - raw_addr));
+        float* headw_s = bias_s + 2 * 256;
         float* headp_s = headw_s + 256;
+        const uint32_t my_staging = staging_addr + ewarp * p.nslots * p.buf_bytes;
+        uint8_t* my_staging_ptr = smem_raw + (my_staging - raw_addr);
+        // Staging buffer = 32 rows x (group x 16) columns of the output type, rows of 32 / 64 / 128 bytes in
+        // the matching TMA swizzle (32B / 64B / 128B): 16-byte piece j of row r sits at j ^ ((r >> shift) & mask),
+        // which makes the row-per-thread accesses below bank-conflict free.
+        const uint32_t row_off = lane * p.row_bytes;
+        const uint32_t row_xor = (lane >> p.piece_shift) & p.piece_mask;
+        const int pieces_per_chunk = p.out_f32 ? 4 : 2;
         if (p.head_w != nullptr && etid < p.block_n) headw_s[etid] = __ldg(p.head_w + etid);  // num_n_tiles == 1
+
         int acc = 0;
         uint32_t acc_phase = 0;
         int buf = 0;
+        uint32_t ngrp = 0;  // staging groups this warp has filled since kernel start (slot = ngrp % nslots)
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_blk = tile / p.num_n_tiles;
             const int n_blk = tile - m_blk * p.num_n_tiles;
             const int n0 = n_blk * p.block_n;
+            const int row0 = m_blk * kBlockM + quarter * 32;  // first output row of this warp
+            const int res_row0 = p.res_rows > 0 ? row0 % p.res_rows : row0;
             float* bs = bias_s + buf * 256;
             if (etid < p.block_n) bs[etid] = p.bias != nullptr ? __ldg(p.bias + n0 + etid) : 0.f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int row = m_blk * kBlockM + row_in_tile;
-            const bool row_ok = row < p.M;
-            const size_t out_off = static_cast<size_t>(row) * p.N + n0;
-            const float* res_row = nullptr;
-            if (p.residual != nullptr && row_ok) {
-                const int rr = p.res_rows > 0 ? (row % p.res_rows) : row;
-                res_row = p.residual + static_cast<size_t>(rr) * p.N + n0;
+
+            auto issue_res_load = [&](uint32_t g, int c) {  // lane 0 only; c = first chunk of the group
+                const int slot = g % kResSlots;
+                const uint32_t bar = res_bar(ewarp, slot);
+                mbar_arrive_expect_tx(bar, p.buf_bytes);
+                tma_load_2d(my_staging + slot * p.buf_bytes, &tmap_res, bar, n0 + c * 16, res_row0);
+            };
+            if (p.has_res && lane == 0) {
+                tma_store_wait_read<1>();  // slots of groups ngrp, ngrp+1 were last read by stores ngrp-3, ngrp-2
+                issue_res_load(ngrp, c_begin);
+                if (n_my > p.group) issue_res_load(ngrp + 1, c_begin + p.group);
             }
-            float4 rnext[4];
-            if (res_row != nullptr) {
-                const float4* r4 = reinterpret_cast<const float4*>(res_row + c_begin * 16);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rnext[i] = r4[i];
-            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // bias staged (double-buffered across tiles)
+
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStageCols;
+            const int row = row0 + lane;
+            const bool row_ok = row < p.M;
             float head_acc = 0.f;
 
             auto process = [&](const uint32_t (&raw)[16], int c) {
-                const int col = c * 16;  // column inside the tile
+                const int col = c * 16;                   // column inside the tile
+                const int k = (c - c_begin) % p.group;    // position of this chunk inside its staging group
+                const int slot = ngrp % p.nslots;
+                uint8_t* stg = my_staging_ptr + slot * p.buf_bytes + row_off;
+                const uint32_t piece0 = k * pieces_per_chunk;
+                if (k == 0) {
+                    if (p.has_res) {
+                        mbar_wait(res_bar(ewarp, ngrp % kResSlots), (ngrp / kResSlots) & 1u);
+                    } else if (p.has_out) {
+                        // the slot was last read by the store issued nslots groups ago
+                        if (lane == 0) tma_store_wait_read<2>();
+                        __syncwarp();
+                    }
+                }
                 float v[16];
                 const float4* b4 = reinterpret_cast<const float4*>(bs + col);
 #pragma unroll
@@ -247,18 +305,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
                 }
-                if (res_row != nullptr) {
+                if (p.has_res) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        v[4 * i + 0] += rnext[i].x;
-                        v[4 * i + 1] += rnext[i].y;
-                        v[4 * i + 2] += rnext[i].z;
-                        v[4 * i + 3] += rnext[i].w;
-                    }
-                    if (c + 1 < c_end) {  // prefetch the next chunk's residual
-                        const float4* r4 = reinterpret_cast<const float4*>(res_row + col + 16);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) rnext[i] = r4[i];
+                        const float4 r = *reinterpret_cast<const float4*>(stg + (((piece0 + i) ^ row_xor) << 4));
+                        v[4 * i + 0] += r.x;
+                        v[4 * i + 1] += r.y;
+                        v[4 * i + 2] += r.z;
+                        v[4 * i + 3] += r.w;
                     }
                 }
                 if (p.head_w != nullptr) {
@@ -272,24 +326,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                         head_acc = fmaf(v[4 * i + 3], w.w, head_acc);
                     }
                 }
-                if (p.out != nullptr && row_ok) {
+                if (p.has_out) {
                     if (p.out_f32) {
-                        float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_off + col);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                            *reinterpret_cast<float4*>(stg + (((piece0 + i) ^ row_xor) << 4)) =
+                                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     } else {
-                        uint4* o4 = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + out_off + col);
-                        o4[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                           pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                        o4[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]),
-                                           pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                        *reinterpret_cast<uint4*>(stg + (((piece0 + 0u) ^ row_xor) << 4)) =
+                            make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                        *reinterpret_cast<uint4*>(stg + (((piece0 + 1u) ^ row_xor) << 4)) =
+                            make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
                     }
+                }
+                if (k == p.group - 1) {  // group complete: publish it
+                    if (p.has_out) {
+                        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + (c - k) * 16, row0);
+                            tma_store_commit();
+                        }
+                    }
+                    if (p.has_res && lane == 0 && c + 1 + p.group < c_end) {
+                        // slot of group ngrp+2 == slot of group ngrp-1: its store must be done reading
+                        tma_store_wait_read<1>();
+                        issue_res_load(ngrp + 2, c + 1 + p.group);
+                    }
+                    ++ngrp;
                 }
             };
 
             uint32_t ra[16], rb[16];
-            if (c_begin < c_end) tmem_ld16(taddr + c_begin * 16, ra);
+            if (n_my > 0) tmem_ld16(taddr + c_begin * 16, ra);
             for (int c = c_begin; c < c_end; c += 2) {
                 tmem_ld_wait();
                 if (c + 1 < c_end) tmem_ld16(taddr + (c + 1) * 16, rb);
@@ -314,6 +383,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             if (acc == 0) acc_phase ^= 1u;
             buf ^= 1;
         }
+        if (lane == 0) tma_store_wait<0>();  // staging smem must outlive the bulk stores
     }
 
     tc_fence_before();
@@ -327,14 +397,20 @@ int pick_block_n(int N) {
     return 0;
 }
 
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, cudaStream_t stream) {
+struct EpiMaps {
+    CUtensorMap out, res;
+};
+
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, cudaStream_t stream) {
     const int stage_bytes = kAStageBytes + a.block_n * 128;
-    int stages = (kSmemBudget - 1024 - 256 - kEpiScratch) / stage_bytes;
+    const int staging = a.has_out ? kEpiWarps * a.nslots * a.buf_bytes : 0;
+    const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
+    int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages > a.num_k_chunks + 1) stages = a.num_k_chunks + 1;  // no point in a deeper ring
     if (stages < 2) stages = 2;
     a.stages = stages;
-    const int smem = stages * stage_bytes + 1024 + 256 + kEpiScratch;
+    const int smem = stages * stage_bytes + fixed;
     static bool attr_set = false;
     if (!attr_set) {
         SPG_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel,
@@ -344,13 +420,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, GemmArgs& a, cudaStream
     const int total = a.num_m_tiles * a.num_n_tiles;
     const int sms = sm_count();
     const int grid = total < sms ? total : sms;
-    gemm_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ta, tb, a);
+    gemm_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ta, tb, em.out, em.res, a);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;
 }
 
-int fill_epilogue(GemmArgs& a, const spg_epilogue_t* ep, int N) {
+int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int N) {
     SPG_CHECK_ARG(ep != nullptr, "epilogue descriptor is NULL");
     SPG_CHECK_ARG(ep->out != nullptr || ep->head_out != nullptr, "epilogue has neither out nor head_out");
     SPG_CHECK_ARG(ep->act >= SPG_ACT_NONE && ep->act <= SPG_ACT_GELU, "unknown activation %d", ep->act);
@@ -358,7 +434,9 @@ int fill_epilogue(GemmArgs& a, const spg_epilogue_t* ep, int N) {
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->out) & 15) == 0, "out must be 16-byte aligned");
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0, "bias must be 16-byte aligned");
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0, "residual must be 16-byte aligned");
-    SPG_CHECK_ARG(ep->res_rows >= 0, "res_rows must be >= 0");
+    SPG_CHECK_ARG(ep->res_rows >= 0 && ep->res_rows % 32 == 0, "res_rows must be a non-negative multiple of 32");
+    if (ep->residual != nullptr)
+        SPG_CHECK_ARG(ep->out != nullptr && ep->out_dtype == SPG_F32, "a residual needs an fp32 output (the residual stream is fp32)");
     if (ep->head_w != nullptr) {
         SPG_CHECK_ARG(ep->head_out != nullptr, "head_w given without head_out");
         SPG_CHECK_ARG(a.block_n == N, "fused head needs the whole row in one tile (N=%d <= 256, N %% 16 == 0)", N);
@@ -366,13 +444,25 @@ int fill_epilogue(GemmArgs& a, const spg_epilogue_t* ep, int N) {
     }
     a.bias = ep->bias;
     a.act = ep->act;
-    a.residual = ep->residual;
+    a.has_res = ep->residual != nullptr;
     a.res_rows = ep->res_rows;
-    a.out = ep->out;
+    a.has_out = ep->out != nullptr;
     a.out_f32 = ep->out_dtype == SPG_F32;
+    a.nslots = kResSlots;
+    // two chunks per staging buffer when each warp's half of the tile is a whole number of pairs
+    a.group = (a.block_n % 64 == 0) ? 2 : 1;
+    a.row_bytes = a.group * 16 * (a.out_f32 ? 4 : 2);
+    a.buf_bytes = 32 * a.row_bytes;
+    a.piece_shift = a.row_bytes == 128 ? 0 : (a.row_bytes == 64 ? 1 : 2);
+    a.piece_mask = a.row_bytes / 16 - 1;
     a.head_w = ep->head_w;
     a.head_b = ep->head_b;
     a.head_out = ep->head_w != nullptr ? ep->head_out : nullptr;
+    memset(&em, 0, sizeof(em));
+    if (a.has_out)
+        if (int rc = make_tmap_epilogue(&em.out, ep->out, M, N, a.out_f32, a.group * 16)) return rc;
+    if (a.has_res)
+        if (int rc = make_tmap_epilogue(&em.res, ep->residual, ep->res_rows > 0 ? ep->res_rows : M, N, 1, a.group * 16)) return rc;
     return SPG_OK;
 }
 
@@ -380,13 +470,14 @@ int fill_epilogue(GemmArgs& a, const spg_epilogue_t* ep, int N) {
 }  // namespace spg
 
 extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
-                               const spg_epilogue_t* ep, spg_stream_t stream) {
+                              const spg_epilogue_t* ep, spg_stream_t stream) {
     using namespace spg;
     SPG_CHECK_ARG(A != nullptr && W != nullptr, "A / W is NULL");
     SPG_CHECK_ARG(M > 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
     SPG_CHECK_ARG(K % 8 == 0, "K=%d must be a multiple of 8 (16-byte TMA row pitch)", K);
     SPG_CHECK_ARG(N % 16 == 0, "N=%d must be a multiple of 16 (UMMA N granularity at M=128)", N);
     GemmArgs a{};
+    EpiMaps em;
     a.M = M;
     a.N = N;
     a.block_n = pick_block_n(N);
@@ -397,15 +488,15 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.H = a.W = 1;
     a.cin_chunks = 1;
     a.tile_w = 1;
-    if (int rc = fill_epilogue(a, ep, N)) return rc;
+    if (int rc = fill_epilogue(a, em, ep, M, N)) return rc;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(K) * 2, kBlockM)) return rc;
     if (int rc = make_tmap_2d(&tb, W, N, K, static_cast<uint64_t>(K) * 2, a.block_n)) return rc;
-    return launch(ta, tb, a, static_cast<cudaStream_t>(stream));
+    return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, int Cout,
-                                const spg_epilogue_t* ep, spg_stream_t stream) {
+                               const spg_epilogue_t* ep, spg_stream_t stream) {
     using namespace spg;
     SPG_CHECK_ARG(x != nullptr && w != nullptr, "x / w is NULL");
     SPG_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad conv shape B=%d H=%d W=%d", B, H, W);
@@ -416,6 +507,7 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     const int tile_h = kBlockM / tile_w;
     SPG_CHECK_ARG(H % tile_h == 0, "H=%d must be a multiple of the tile height %d", H, tile_h);
     GemmArgs a{};
+    EpiMaps em;
     a.M = B * H * W;
     a.N = Cout;
     a.block_n = pick_block_n(Cout);
@@ -427,9 +519,9 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     a.H = H;
     a.W = W;
     a.tile_w = tile_w;
-    if (int rc = fill_epilogue(a, ep, Cout)) return rc;
+    if (int rc = fill_epilogue(a, em, ep, a.M, Cout)) return rc;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, tile_h, tile_w)) return rc;
     if (int rc = make_tmap_2d(&tb, w, Cout, 9ull * Cin, 18ull * Cin, a.block_n)) return rc;
-    return launch(ta, tb, a, static_cast<cudaStream_t>(stream));
+    return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
 }
