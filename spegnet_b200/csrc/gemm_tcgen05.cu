@@ -62,7 +62,6 @@ struct GemmArgs {
     int res_rows;
     int has_out;
     int out_f32;
-    int nslots;       // staging ring depth per epilogue warp (kResSlots)
     int group;        // 16-column chunks per staging buffer / TMA op (1 or 2)
     int row_bytes;    // bytes per staging row = group * 16 * sizeof(out)   (32 / 64 / 128)
     int buf_bytes;    // 32 * row_bytes
@@ -92,10 +91,18 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(hx, erf_z, hx);
 }
 
+// Epilogue traits are compile-time constants for the combinations the model launches (the hot loop then
+// carries no flag tests); -1 selects the run-time value from GemmArgs (generic fallback instance).
+template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmArgs p) {
+    const int act = kAct < 0 ? p.act : kAct;
+    const bool out_f32 = kOutF32 < 0 ? p.out_f32 != 0 : kOutF32 != 0;
+    const bool has_res = kHasRes < 0 ? p.has_res != 0 : kHasRes != 0;
+    const bool has_head = kHasHead < 0 ? p.head_w != nullptr : kHasHead != 0;
+    const bool has_out = kHasOut < 0 ? p.has_out != 0 : kHasOut != 0;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
@@ -118,8 +125,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        if (p.has_out) tma_prefetch_desc(&tmap_out);
-        if (p.has_res) tma_prefetch_desc(&tmap_res);
+        if (has_out) tma_prefetch_desc(&tmap_out);
+        if (has_res) tma_prefetch_desc(&tmap_res);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -230,20 +237,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float* bias_s = reinterpret_cast<float*>(smem_raw + (scratch_addr - raw_addr));
         float* headw_s = bias_s + 2 * 256;
         float* headp_s = headw_s + 256;
-        const uint32_t my_staging = staging_addr + ewarp * p.nslots * p.buf_bytes;
+        const uint32_t my_staging = staging_addr + ewarp * kResSlots * p.buf_bytes;
         uint8_t* my_staging_ptr = smem_raw + (my_staging - raw_addr);
         // Staging buffer = 32 rows x (group x 16) columns of the output type, rows of 32 / 64 / 128 bytes in
         // the matching TMA swizzle (32B / 64B / 128B): 16-byte piece j of row r sits at j ^ ((r >> shift) & mask),
         // which makes the row-per-thread accesses below bank-conflict free.
         const uint32_t row_off = lane * p.row_bytes;
         const uint32_t row_xor = (lane >> p.piece_shift) & p.piece_mask;
-        const int pieces_per_chunk = p.out_f32 ? 4 : 2;
-        if (p.head_w != nullptr && etid < p.block_n) headw_s[etid] = __ldg(p.head_w + etid);  // num_n_tiles == 1
+        const uint32_t pieces_per_chunk = out_f32 ? 4u : 2u;
+        const bool pair = p.group == 2;  // two 16-column chunks share one staging buffer / TMA op
+        if (has_head && etid < p.block_n) headw_s[etid] = __ldg(p.head_w + etid);  // num_n_tiles == 1
 
         int acc = 0;
         uint32_t acc_phase = 0;
         int buf = 0;
-        uint32_t ngrp = 0;  // staging groups this warp has filled since kernel start (slot = ngrp % nslots)
+        // staging ring state: slot of the group being filled, per-slot residual-barrier parity (bit i = slot i),
+        // and the slot / parity bookkeeping of the residual loads running two groups ahead
+        int slot = 0;
+        uint32_t res_parity = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_blk = tile / p.num_n_tiles;
             const int n_blk = tile - m_blk * p.num_n_tiles;
@@ -253,16 +264,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             float* bs = bias_s + buf * 256;
             if (etid < p.block_n) bs[etid] = p.bias != nullptr ? __ldg(p.bias + n0 + etid) : 0.f;
 
-            auto issue_res_load = [&](uint32_t g, int c) {  // lane 0 only; c = first chunk of the group
-                const int slot = g % kResSlots;
-                const uint32_t bar = res_bar(ewarp, slot);
+            auto issue_res_load = [&](int sl, int c) {  // lane 0 only; c = first chunk of the group
+                const uint32_t bar = res_bar(ewarp, sl);
                 mbar_arrive_expect_tx(bar, p.buf_bytes);
-                tma_load_2d(my_staging + slot * p.buf_bytes, &tmap_res, bar, n0 + c * 16, res_row0);
+                tma_load_2d(my_staging + sl * p.buf_bytes, &tmap_res, bar, n0 + c * 16, res_row0);
             };
-            if (p.has_res && lane == 0) {
-                tma_store_wait_read<1>();  // slots of groups ngrp, ngrp+1 were last read by stores ngrp-3, ngrp-2
-                issue_res_load(ngrp, c_begin);
-                if (n_my > p.group) issue_res_load(ngrp + 1, c_begin + p.group);
+            const int slot1 = slot == kResSlots - 1 ? 0 : slot + 1;
+            if (has_res && lane == 0) {
+                tma_store_wait_read<1>();  // these two slots were last read by the stores 3 and 2 groups ago
+                issue_res_load(slot, c_begin);
+                if (n_my > p.group) issue_res_load(slot1, c_begin + p.group);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");  // bias staged (double-buffered across tiles)
 
@@ -273,18 +284,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const bool row_ok = row < p.M;
             float head_acc = 0.f;
 
-            auto process = [&](const uint32_t (&raw)[16], int c) {
-                const int col = c * 16;                   // column inside the tile
-                const int k = (c - c_begin) % p.group;    // position of this chunk inside its staging group
-                const int slot = ngrp % p.nslots;
+            // first / last: position of this chunk inside its staging group
+            auto process = [&](const uint32_t (&raw)[16], int c, bool first, bool last) {
+                const int col = c * 16;  // column inside the tile
                 uint8_t* stg = my_staging_ptr + slot * p.buf_bytes + row_off;
-                const uint32_t piece0 = k * pieces_per_chunk;
-                if (k == 0) {
-                    if (p.has_res) {
-                        mbar_wait(res_bar(ewarp, ngrp % kResSlots), (ngrp / kResSlots) & 1u);
-                    } else if (p.has_out) {
-                        // the slot was last read by the store issued nslots groups ago
-                        if (lane == 0) tma_store_wait_read<2>();
+                const uint32_t piece0 = first ? 0u : pieces_per_chunk;
+                if (first) {
+                    if (has_res) {
+                        mbar_wait(res_bar(ewarp, slot), (res_parity >> slot) & 1u);
+                        res_parity ^= 1u << slot;
+                    } else if (has_out) {
+                        // the slot was last read by the store issued kResSlots groups ago
+                        if (lane == 0) tma_store_wait_read<kResSlots - 1>();
                         __syncwarp();
                     }
                 }
@@ -298,14 +309,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
                     v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
                 }
-                if (p.act == SPG_ACT_RELU) {
+                if (act == SPG_ACT_RELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-                } else if (p.act == SPG_ACT_GELU) {
+                } else if (act == SPG_ACT_GELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
                 }
-                if (p.has_res) {
+                if (has_res) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 r = *reinterpret_cast<const float4*>(stg + (((piece0 + i) ^ row_xor) << 4));
@@ -315,7 +326,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         v[4 * i + 3] += r.w;
                     }
                 }
-                if (p.head_w != nullptr) {
+                if (has_head) {
                     const float4* w4 = reinterpret_cast<const float4*>(headw_s + col);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -326,8 +337,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         head_acc = fmaf(v[4 * i + 3], w.w, head_acc);
                     }
                 }
-                if (p.has_out) {
-                    if (p.out_f32) {
+                if (has_out) {
+                    if (out_f32) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             *reinterpret_cast<float4*>(stg + (((piece0 + i) ^ row_xor) << 4)) =
@@ -339,21 +350,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
                     }
                 }
-                if (k == p.group - 1) {  // group complete: publish it
-                    if (p.has_out) {
+                if (last) {  // group complete: publish it
+                    const int c_first = first ? c : c - 1;
+                    if (has_out) {
                         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + (c - k) * 16, row0);
+                            tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, row0);
                             tma_store_commit();
                         }
                     }
-                    if (p.has_res && lane == 0 && c + 1 + p.group < c_end) {
-                        // slot of group ngrp+2 == slot of group ngrp-1: its store must be done reading
+                    if (has_res && lane == 0 && c + 1 + p.group < c_end) {
+                        // the group two ahead reuses the slot of the previous group: its store must be done reading
                         tma_store_wait_read<1>();
-                        issue_res_load(ngrp + 2, c + 1 + p.group);
+                        issue_res_load(slot == 0 ? kResSlots - 1 : slot - 1, c + 1 + p.group);
                     }
-                    ++ngrp;
+                    slot = slot == kResSlots - 1 ? 0 : slot + 1;
                 }
             };
 
@@ -362,18 +374,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int c = c_begin; c < c_end; c += 2) {
                 tmem_ld_wait();
                 if (c + 1 < c_end) tmem_ld16(taddr + (c + 1) * 16, rb);
-                process(ra, c);
+                process(ra, c, true, !pair);
                 if (c + 1 < c_end) {
                     tmem_ld_wait();
                     if (c + 2 < c_end) tmem_ld16(taddr + (c + 2) * 16, ra);
-                    process(rb, c + 1);
+                    process(rb, c + 1, !pair, true);
                 }
             }
             // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-            if (p.head_w != nullptr) {
+            if (has_head) {
                 // combine the two column halves of the fused N->1 head through smem
                 if (half == 1) headp_s[row_in_tile] = head_acc;
                 asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -403,7 +415,7 @@ struct EpiMaps {
 
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, cudaStream_t stream) {
     const int stage_bytes = kAStageBytes + a.block_n * 128;
-    const int staging = a.has_out ? kEpiWarps * a.nslots * a.buf_bytes : 0;
+    const int staging = a.has_out ? kEpiWarps * kResSlots * a.buf_bytes : 0;
     const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -411,16 +423,30 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     if (stages < 2) stages = 2;
     a.stages = stages;
     const int smem = stages * stage_bytes + fixed;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SPG_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-        attr_set = true;
-    }
     const int total = a.num_m_tiles * a.num_n_tiles;
     const int sms = sm_count();
     const int grid = total < sms ? total : sms;
-    gemm_tcgen05_kernel<<<grid, kThreads, smem, stream>>>(ta, tb, em.out, em.res, a);
+    const bool head = a.head_w != nullptr;
+    // the combinations SPEGNet launches get a compile-time specialised epilogue; anything else runs the generic one
+#define SPG_LAUNCH(ACT, F32, RES, HEAD, OUT)                                                                       \
+    do {                                                                                                           \
+        auto kern = gemm_tcgen05_kernel<ACT, F32, RES, HEAD, OUT>;                                                 \
+        static bool attr_set = false;                                                                              \
+        if (!attr_set) {                                                                                           \
+            SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
+            attr_set = true;                                                                                       \
+        }                                                                                                          \
+        kern<<<grid, kThreads, smem, stream>>>(ta, tb, em.out, em.res, a);                                         \
+    } while (0)
+    if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 0, 0, 0, 1);
+    else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1);
+    else if (a.act == SPG_ACT_NONE && a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 0, 0, 1);
+    else if (a.act == SPG_ACT_GELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_GELU, 0, 0, 0, 1);
+    else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_RELU, 0, 0, 0, 1);
+    else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && head && a.has_out) SPG_LAUNCH(SPG_ACT_RELU, 0, 0, 1, 1);
+    else if (a.act == SPG_ACT_RELU && !a.has_res && head && !a.has_out) SPG_LAUNCH(SPG_ACT_RELU, 0, 0, 1, 0);
+    else SPG_LAUNCH(-1, -1, -1, -1, -1);
+#undef SPG_LAUNCH
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;
@@ -448,7 +474,6 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
     a.res_rows = ep->res_rows;
     a.has_out = ep->out != nullptr;
     a.out_f32 = ep->out_dtype == SPG_F32;
-    a.nslots = kResSlots;
     // two chunks per staging buffer when each warp's half of the tile is a whole number of pairs
     a.group = (a.block_n % 64 == 0) ? 2 : 1;
     a.row_bytes = a.group * 16 * (a.out_f32 ? 4 : 2);
