@@ -204,15 +204,18 @@ def main():
     # per-step activation working set (~13 GB at B=64) is two orders of magnitude beyond the 126 MB L2.
     batches = [torch.randn(B, 3, S, S, device=dev, generator=gen) for _ in range(3)]
 
+    gt = (torch.rand(B, S, S, device=dev, generator=gen) > 0.75).to(torch.uint8) * 255  # synthetic ground truth
+
     def step(i):
         out = model(batches[i % 3])
-        # metric partial: per-image mean foreground probability proxy (sum of logits), gathered across ranks
-        part = out["predictions"][-1].sum(dim=(1, 2, 3))
+        # per-image predictions -> uint8 masks + integer MAE partials on the GPU (utils/metrics.py:205-210), and the
+        # only collective of the path: one all_gather of 5 integers per image
+        _, stats = ops.mask_stats(out["predictions"][-1], gt, True)
         if dist is not None:
-            gathered = torch.empty(world * B, device=dev)
-            dist.all_gather_into_tensor(gathered, part)
+            gathered = torch.empty(world * B, stats.shape[1], dtype=stats.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, stats)
             return gathered
-        return part
+        return stats
 
     # ---- instrumented GEMM/conv timing (dominant kernel) -------------------------------------------------
     gemm_events = []

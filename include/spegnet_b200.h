@@ -171,6 +171,17 @@ int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, con
                        const float* wf_bias, void* y, int B, int H, int W, const int* dilations,
                        spg_stream_t stream);
 
+/*
+ * Mask quantisation of the reference's metric wrapper on the GPU (utils/metrics.py:205-210): mask = uint8(
+ * sigmoid(logit) * 255) with truncation (double_sigmoid = 1: sigmoid applied twice, the evaluator path,
+ * engine/evaluator.py:544 + utils/metrics.py:209), gt is uint8 with foreground > 128.  stats[b][8] (uint32) =
+ * {255 - min q, max q, #gt foreground, sum q over gt background, sum q over gt foreground, 0, 0, 0}: integer
+ * partials from which MAE after the min-max normalisation of py_sod_metrics follows exactly; they are what the
+ * ranks all_gather in the sharded evaluation (8 x 4 bytes per image instead of the mask).
+ */
+int spg_mask_stats_u8(const float* logits, const unsigned char* gt, unsigned char* mask, unsigned* stats, int B,
+                      int HW, int double_sigmoid, spg_stream_t stream);
+
 /* bf16 NHWC [B,HW,C] -> fp32 NCHW [B,C,HW] (materialises `features` entries of the output dict on demand). */
 int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream);
 

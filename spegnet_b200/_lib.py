@@ -50,6 +50,7 @@ SIGNATURES = {
     "spg_scale_channels_h16": [_P, _P, _I, _I, _I, _P],
     "spg_easpp_branches": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(C.c_int), _P],
     "spg_nhwc_h16_to_nchw_f32": [_P, _P, _I, _I, _I, _P],
+    "spg_mask_stats_u8": [_P, _P, _P, _P, _I, _I, _I, _P],
     "spg_device_check": [],
     "spg_version": [],
     "spg_half_is_fp16": [],

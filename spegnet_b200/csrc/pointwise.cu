@@ -373,6 +373,54 @@ nhwc_to_nchw_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, int H
     y[idx] = h_to_float(x[(b * HW + p) * C + c]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Mask quantisation exactly as the reference's metric wrapper (utils/metrics.py:205-210): q = uint8(sigmoid(x)
+// * 255) with truncation (optionally sigmoid twice: the evaluator path, engine/evaluator.py:544), plus the
+// per-image integer statistics from which MAE after min-max normalisation follows exactly:
+//   stats[b] = { 255 - min q, max q, #gt_fg, sum q over gt background, sum q over gt foreground }
+// Integer atomics only, so the result is independent of scheduling.  4 pixels per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_stats_kernel(const float4* __restrict__ logits, const uchar4* __restrict__ gt, uchar4* __restrict__ mask,
+                  unsigned* __restrict__ stats, int HW4, int double_sigmoid) {
+    const int b = blockIdx.y;
+    unsigned inv_min = 0, mx = 0, nfg = 0, sbg = 0, sfg = 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < HW4; i += gridDim.x * 256) {
+        const float4 x = logits[static_cast<size_t>(b) * HW4 + i];
+        const uchar4 g = gt[static_cast<size_t>(b) * HW4 + i];
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+        const unsigned char gs[4] = {g.x, g.y, g.z, g.w};
+        unsigned char qs[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float p = 1.f / (1.f + expf(-xs[k]));
+            if (double_sigmoid) p = 1.f / (1.f + expf(-p));
+            const unsigned q = static_cast<unsigned>(p * 255.f);
+            qs[k] = static_cast<unsigned char>(q);
+            inv_min = max(inv_min, 255u - q);
+            mx = max(mx, q);
+            if (gs[k] > 128) { ++nfg; sfg += q; } else { sbg += q; }
+        }
+        mask[static_cast<size_t>(b) * HW4 + i] = make_uchar4(qs[0], qs[1], qs[2], qs[3]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        inv_min = max(inv_min, __shfl_xor_sync(0xffffffffu, inv_min, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        nfg += __shfl_xor_sync(0xffffffffu, nfg, o);
+        sbg += __shfl_xor_sync(0xffffffffu, sbg, o);
+        sfg += __shfl_xor_sync(0xffffffffu, sfg, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned* st = stats + b * 8;
+        atomicMax(st + 0, inv_min);
+        atomicMax(st + 1, mx);
+        atomicAdd(st + 2, nfg);
+        atomicAdd(st + 3, sbg);
+        atomicAdd(st + 4, sfg);
+    }
+}
+
 inline unsigned blocks_for(long long total, int per_block = 256) {
     return static_cast<unsigned>((total + per_block - 1) / per_block);
 }
@@ -480,6 +528,20 @@ extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* d
                  {dilations[0], dilations[1], dilations[2], dilations[3]}};
     const long long total = static_cast<long long>(B) * H * W * 16;
     aspp_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_mask_stats_u8(const float* logits, const unsigned char* gt, unsigned char* mask, unsigned* stats,
+                                 int B, int HW, int double_sigmoid, spg_stream_t stream) {
+    SPG_CHECK_ARG(logits && gt && mask && stats, "null pointer");
+    SPG_CHECK_ARG(B > 0 && HW > 0 && HW % 4 == 0, "mask_stats needs HW %% 4 == 0");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SPG_CHECK_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * 8 * sizeof(unsigned), st));
+    const int per_img = min(64, (HW / 4 + 255) / 256);
+    mask_stats_kernel<<<dim3(per_img, B), 256, 0, st>>>(reinterpret_cast<const float4*>(logits),
+                                                        reinterpret_cast<const uchar4*>(gt),
+                                                        reinterpret_cast<uchar4*>(mask), stats, HW / 4, double_sigmoid);
     SPG_LAUNCHED();
     return SPG_OK;
 }

@@ -183,3 +183,30 @@ def nhwc_to_nchw_f32(x: torch.Tensor, y: torch.Tensor, B: int, HW: int, Cc: int)
     rc = lib.spg_nhwc_h16_to_nchw_f32(_ptr(x, H16, "x"), _ptr(y, torch.float32, "y"), B, HW, Cc,
                                                _stream())
     _lib.check(rc, "spg_nhwc_h16_to_nchw_f32", dn)
+
+
+def mask_stats(logits: torch.Tensor, gt_u8: torch.Tensor, double_sigmoid: bool = False):
+    """logits [B,1,H,W] fp32, gt_u8 [B,H,W] uint8 (foreground > 128) -> (mask uint8 [B,H,W], stats int64 [B,5]).
+    See spg_mask_stats_u8; `mae_from_stats` turns the statistics into the reference's MAE."""
+    B = logits.shape[0]
+    HW = logits[0].numel()
+    mask = torch.empty(B, *gt_u8.shape[1:], dtype=torch.uint8, device=logits.device)
+    stats = torch.empty(B, 8, dtype=torch.int32, device=logits.device)
+    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    rc = lib.spg_mask_stats_u8(_ptr(logits, torch.float32, "logits"), _ptr(gt_u8, torch.uint8, "gt"),
+                               _ptr(mask, torch.uint8, "mask"), _ptr(stats, torch.int32, "stats"), B, HW,
+                               int(double_sigmoid), _stream())
+    _lib.check(rc, "spg_mask_stats_u8", dn)
+    return mask, stats[:, :5].to(torch.int64)
+
+
+def mae_from_stats(stats: torch.Tensor, n_pixels: int) -> torch.Tensor:
+    """Per-image MAE of py_sod_metrics (pred / 255, min-max normalised unless constant; gt > 128) from the integer
+    statistics of `mask_stats`, in fp64: exact, and identical on any number of GPUs."""
+    s = stats.to(torch.float64)
+    lo, hi, nfg, sbg, sfg = 255.0 - s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 4]
+    nbg = n_pixels - nfg
+    span = hi - lo
+    norm = ((sbg - lo * nbg) + (hi * nfg - sfg)) / torch.where(span > 0, span, torch.ones_like(span))
+    flat = sbg / 255.0 + (nfg - sfg / 255.0)
+    return torch.where(span > 0, norm, flat) / n_pixels

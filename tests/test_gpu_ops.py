@@ -257,3 +257,29 @@ def test_nhwc_to_nchw(ops):
     y = torch.empty(2, 64, 8, 8, device="cuda")
     ops.nhwc_to_nchw_f32(x, y, 2, 64, 64)
     assert torch.equal(y, x.float().permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("double_sigmoid", [False, True])
+def test_mask_stats_match_reference_quantisation_and_mae(ops, double_sigmoid):
+    """uint8 mask + integer statistics on the GPU vs the oracle's quantisation and MAE (utils/metrics.py:205-210)."""
+    import numpy as np
+
+    from oracle import sod_metrics as M
+
+    g = torch.Generator().manual_seed(12)
+    logits = torch.randn(3, 1, 64, 64, generator=g) * 2.5 - 1.0
+    gt = (torch.rand(3, 64, 64, generator=g) > 0.7).to(torch.uint8) * 255
+    logits[2] = 0.3  # a constant prediction exercises the "no min-max normalisation" branch
+    mask, stats = ops.mask_stats(logits.cuda(), gt.cuda(), double_sigmoid)
+    mae = ops.mae_from_stats(stats, 64 * 64).cpu().numpy()
+    for i in range(3):
+        x = logits[i, 0].numpy()
+        if double_sigmoid:
+            x = 1 / (1 + np.exp(-x))
+        ref_q = M.quantise_like_reference(x)
+        got_q = mask[i].cpu().numpy()
+        # expf vs numpy exp may disagree by one grey level exactly at a truncation boundary
+        assert np.abs(got_q.astype(int) - ref_q.astype(int)).max() <= 1
+        assert (got_q != ref_q).mean() < 2e-3
+        ref_mae = M.score_pair(got_q, gt[i].numpy())["mae"]  # same mask -> the statistics must give the exact MAE
+        assert abs(mae[i] - ref_mae) < 1e-12
