@@ -76,13 +76,15 @@ template <int KB>  // keys consumed per softmax step (16 or 64)
 __global__ void __launch_bounds__(kThreads)
 window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t kv_bar;
+    // K/V arrive in up to four independent units (64 keys, or one small window) with one mbarrier each, so
+    // the first QK^T tiles start while the rest of the window is still in flight
+    __shared__ __align__(8) uint64_t kv_bar[4];
     const uint32_t Ks_u = (smem_u32(smem) + 127u) & ~127u;  // TMA destinations: 128-byte aligned
     const uint32_t Vs_u = Ks_u + kRowsSmem * kHd * 2;
-    const uint32_t bar_u = smem_u32(&kv_bar);
+    const uint32_t bar_u = smem_u32(&kv_bar[0]);
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_kv);
-        mbar_init(bar_u, 1);
+        for (int u = 0; u < 4; ++u) mbar_init(bar_u + 8u * u, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -153,22 +155,25 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
     for (int kbase = 0; kbase < rows_total; kbase += kRowsSmem) {
         const int rows = min(kRowsSmem, rows_total - kbase);
         if (kbase > 0) __syncthreads();  // everyone is done with the previous K/V pass
-        // ---- stage K and V rows with TMA: one box per (window, K|V); a pass covers box_h window rows
+        // ---- stage K and V rows with TMA: unit u = one box per K and per V, signalling barrier u
+        const uint32_t pass_parity = static_cast<uint32_t>(kbase / kRowsSmem) & 1u;
         if (threadIdx.x == 0) {
-            const int nbox = p.wpc > 1 ? p.wpc : 1;
-            mbar_arrive_expect_tx(bar_u, static_cast<uint32_t>(rows) * kHd * 2u * 2u);
-            for (int w = 0; w < nbox; ++w) {
-                const int kw = win0 + w;
+            const int unit_rows = p.ws * p.box_h;  // 64 keys, or a whole small window
+            const int nunits = rows / unit_rows;
+            for (int u = 0; u < nunits; ++u) {
+                // quad mode: unit = window win0+u; otherwise unit = box_h consecutive rows of this window
+                const int kw = p.wpc > 1 ? win0 + u : win0;
                 const int kb = kw / wins_per_img;
                 const int kwr = kw - kb * wins_per_img;
                 const int kwy = kwr / p.nwx, kwx = kwr - kwy * p.nwx;
-                const int y = kwy * p.ws + (p.wpc > 1 ? 0 : (kbase / p.ws));
-                const uint32_t dst_off = static_cast<uint32_t>(w) * p.Nk * kHd * 2u;
-                tma_load_4d(Ks_u + dst_off, &tmap_kv, bar_u, p.D + head * kHd, kwx * p.ws, y, kb);
-                tma_load_4d(Vs_u + dst_off, &tmap_kv, bar_u, 2 * p.D + head * kHd, kwx * p.ws, y, kb);
+                const int y = kwy * p.ws + (p.wpc > 1 ? 0 : (kbase / p.ws + u * p.box_h));
+                const uint32_t dst_off = static_cast<uint32_t>(u) * unit_rows * kHd * 2u;
+                const uint32_t bar = bar_u + 8u * u;
+                mbar_arrive_expect_tx(bar, static_cast<uint32_t>(unit_rows) * kHd * 2u * 2u);
+                tma_load_4d(Ks_u + dst_off, &tmap_kv, bar, p.D + head * kHd, kwx * p.ws, y, kb);
+                tma_load_4d(Vs_u + dst_off, &tmap_kv, bar, 2 * p.D + head * kHd, kwx * p.ws, y, kb);
             }
         }
-        mbar_wait(bar_u, static_cast<uint32_t>(kbase / kRowsSmem) & 1u);
 
         // ---- this warp's slice of the staged rows
         int kbeg = 0, kend = rows;
@@ -179,6 +184,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
         if (warp_active) {
             for (int k0 = kbeg; k0 < kend; k0 += KB) {
                 constexpr int NT = KB / 8;
+                mbar_wait(bar_u + 8u * (p.wpc > 1 ? warp : (k0 >> 6)), pass_parity);  // this unit has landed
                 float s[NT][4];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
@@ -378,8 +384,8 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     }
     p.wpc = p.Nq < 64 ? 4 : 1;  // one window per warp; rows >= Nq of a warp's 16-row tile are masked off
     p.qtiles = p.Nq >= 64 ? p.Nq / 64 : 1;
-    p.box_h = p.Nk <= kRowsSmem ? ws : kRowsSmem / ws;
-    SPG_CHECK_ARG(ws <= 256 && p.box_h >= 1 && ws * p.box_h <= kRowsSmem, "window %d too wide for the K/V staging", ws);
+    p.box_h = p.Nk <= 64 ? ws : 64 / ws;  // a unit is 64 keys (or the whole window when it is smaller)
+    SPG_CHECK_ARG(ws <= 64 && p.box_h >= 1, "window %d too wide for the K/V staging", ws);
     CUtensorMap tmap;
     if (int rc = make_tmap_qkv_window(&tmap, qkv, B, H, W, 3 * D, kHd, ws, p.box_h)) return rc;
     const int smem = 2 * kRowsSmem * kHd * 2 + 128;

@@ -37,6 +37,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
+constexpr int kHaloABytes = 17 * 1024;  // 130 halo pixels x 128 B = 16640 B, padded to a 1 KB multiple
 constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kEpiWarps = 8;
 constexpr int kTmemCols = 512;
@@ -52,6 +53,7 @@ struct GemmArgs {
     int block_n;
     int num_m_tiles, num_n_tiles, num_k_chunks;
     int stages;
+    int halo;        // conv only: one stage = a 130-pixel halo row of A + the 3 dx-tap weight tiles (A reuse x3)
     // conv mode
     int conv;
     int H, W, cin_chunks, tile_w;
@@ -107,7 +109,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
     const uint32_t b_stage_bytes = static_cast<uint32_t>(p.block_n) * 128u;
-    const uint32_t stage_bytes = kAStageBytes + b_stage_bytes;
+    // halo mode: A stage = 130 pixels x 128 B (padded to 17 KB so stages stay 1 KB aligned) + three weight tiles
+    const uint32_t a_stage_bytes = p.halo ? kHaloABytes : kAStageBytes;
+    const uint32_t stage_bytes = a_stage_bytes + (p.halo ? 3u : 1u) * b_stage_bytes;
     const uint32_t bar_addr = tiles_addr + static_cast<uint32_t>(p.stages) * stage_bytes;
     auto full_bar = [&](int s) { return bar_addr + 8u * s; };
     auto empty_bar = [&](int s) { return bar_addr + 8u * (p.stages + s); };
@@ -169,7 +173,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int kc = 0; kc < p.num_k_chunks; ++kc) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = tiles_addr + stage * stage_bytes;
-                    const uint32_t b_dst = a_dst + kAStageBytes;
+                    const uint32_t b_dst = a_dst + a_stage_bytes;
+                    if (p.halo) {
+                        // k-chunk = (dy, 64-channel chunk): one 130-pixel halo row serves the taps dx = -1, 0, +1
+                        const int dyi = kc / p.cin_chunks;
+                        const int cc = kc - dyi * p.cin_chunks;
+                        mbar_arrive_expect_tx(full_bar(stage), 130u * 128u + 3u * b_stage_bytes);
+                        tma_load_4d(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 - 1, y0 + dyi - 1, img);
+#pragma unroll
+                        for (int dxi = 0; dxi < 3; ++dxi)
+                            tma_load_2d(b_dst + dxi * b_stage_bytes, &tmap_b, full_bar(stage),
+                                        ((dyi * 3 + dxi) * p.cin_chunks + cc) * kBlockK, n_blk * p.block_n);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
                     if (p.conv) {
                         const int tap = kc / p.cin_chunks;
@@ -204,13 +224,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t a_addr = tiles_addr + stage * stage_bytes;
-                    const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-                    const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kAStageBytes);
+                    if (p.halo) {
+                        // tap dx reads the same halo rows shifted by dx pixels: start address + dx * 128 B.  The 128 B
+                        // swizzle is a function of absolute smem address bits, so a start that is not 1024 B aligned
+                        // needs no base offset in the descriptor (measured: base_offset 0 is the convention that
+                        // reproduces the reference, tests/cuda/test_gemm.cu)
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance 32 B (= 16 elements) along K inside the 128 B swizzle atom
-                        const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                        umma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (kc | k) != 0);
+                        for (int dxi = 0; dxi < 3; ++dxi) {
+                            const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + dxi * 128u);
+                            const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + a_stage_bytes + dxi * b_stage_bytes);
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+                                umma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (kc | dxi | k) != 0);
+                            }
+                        }
+                    } else {
+                        const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+                        const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kAStageBytes);
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            // advance 32 B (= 16 elements) along K inside the 128 B swizzle atom
+                            const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
+                            umma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (kc | k) != 0);
+                        }
                     }
                     umma_commit(empty_bar(stage));
                     if (++stage == p.stages) {
@@ -414,7 +451,7 @@ struct EpiMaps {
 };
 
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, cudaStream_t stream) {
-    const int stage_bytes = kAStageBytes + a.block_n * 128;
+    const int stage_bytes = a.halo ? kHaloABytes + 3 * a.block_n * 128 : kAStageBytes + a.block_n * 128;
     const int staging = a.has_out ? kEpiWarps * kResSlots * a.buf_bytes : 0;
     const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
     int stages = (kSmemBudget - fixed) / stage_bytes;
@@ -475,7 +512,7 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
     a.has_out = ep->out != nullptr;
     a.out_f32 = ep->out_dtype == SPG_F32;
     // two chunks per staging buffer when each warp's half of the tile is a whole number of pairs
-    a.group = (a.block_n % 64 == 0) ? 2 : 1;
+    a.group = (a.block_n % 64 == 0 && !a.has_res) ? 2 : 1;  // with a residual: 2 KB buffers -> one more mainloop stage
     a.row_bytes = a.group * 16 * (a.out_f32 ? 4 : 2);
     a.buf_bytes = 32 * a.row_bytes;
     a.piece_shift = a.row_bytes == 128 ? 0 : (a.row_bytes == 64 ? 1 : 2);
@@ -544,9 +581,14 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     a.H = H;
     a.W = W;
     a.tile_w = tile_w;
+    // Row-halo mode (tile = 128 pixels of one image row, narrow N): the ring is bound by bytes in flight over a
+    // ~2-3 us TMA round trip, so A is loaded once per (dy, channel chunk) as a 130-pixel halo row and reused by
+    // the three dx taps through shifted descriptors: 1.5-1.9x fewer bytes per FLOP than one A tile per tap.
+    a.halo = (tile_h == 1 && a.block_n <= 128) ? 1 : 0;
+    if (a.halo) a.num_k_chunks = 3 * a.cin_chunks;
     if (int rc = fill_epilogue(a, em, ep, a.M, Cout)) return rc;
     CUtensorMap ta, tb;
-    if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, tile_h, tile_w)) return rc;
+    if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, tile_h, a.halo ? 130 : tile_w)) return rc;
     if (int rc = make_tmap_2d(&tb, w, Cout, 9ull * Cin, 18ull * Cin, a.block_n)) return rc;
     return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
 }

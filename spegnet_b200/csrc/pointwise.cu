@@ -27,47 +27,59 @@ __device__ __forceinline__ float warp_sum(float v) {
 // LayerNorm over the channel axis: fp32 residual stream in, bf16 GEMM operand out. One warp per token,
 // the row lives in registers (two-pass variance), C <= 1152.
 // ------------------------------------------------------------------------------------------------
-constexpr int kLnMaxVec = 9;  // 9 float4 per lane * 32 lanes * 4 = 1152 channels
+constexpr int kLnMaxC = 1152;
 
+// LPR = lanes cooperating on one row (32, or 16 for C <= 256 so that a 144-channel row does not idle half a warp);
+// each warp walks over `rows_per_warp` consecutive row groups so that a block moves >= 64 KB.
+template <int LPR, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, uint16_t* __restrict__ y,
-                                                        int M, int C, float eps) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= M) return;
-    const int lane = threadIdx.x & 31;
+                                                        int M, int C, float eps, int rows_per_warp) {
+    constexpr int RPW = 32 / LPR;  // rows processed concurrently by one warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane % LPR, grp = lane / LPR;
     const int nvec = C >> 2;
-    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * C);
-    float4 v[kLnMaxVec];
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-        const int j = lane + 32 * i;
-        if (j < nvec) {
-            v[i] = xr[j];
-            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-        }
-    }
-    const float mean = warp_sum(s) / C;
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-        const int j = lane + 32 * i;
-        if (j < nvec) {
-            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-            q += (a * a + b * b) + (c * c + d * d);
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(q) / C + eps);
-    uint2* yr = reinterpret_cast<uint2*>(y + static_cast<size_t>(row) * C);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
+    const long long first = (static_cast<long long>(blockIdx.x) * 8 + warp) * rows_per_warp * RPW;
+    for (int it = 0; it < rows_per_warp; ++it) {
+        const long long row = first + it * RPW + grp;
+        const bool ok = row < M;
+        const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+        float4 v[MAXV];
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxVec; ++i) {
-        const int j = lane + 32 * i;
-        if (j < nvec) {
-            const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-            yr[j] = make_uint2(pack2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
-                               pack2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = sub + LPR * i;
+            if (ok && j < nvec) {
+                v[i] = xr[j];
+                s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = sub + LPR * i;
+            if (ok && j < nvec) {
+                const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+                q += (a * a + b * b) + (c * c + d * d);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / C + eps);
+        uint2* yr = reinterpret_cast<uint2*>(y + row * C);
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int j = sub + LPR * i;
+            if (ok && j < nvec) {
+                const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+                yr[j] = make_uint2(pack2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y),
+                                   pack2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w));
+            }
         }
     }
 }
@@ -79,26 +91,26 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, uint16_t* __restrict__ cols, int B,
                                                        int S) {
     const int G = S >> 2;
-    const long long idx = blockIdx.x * 256ll + threadIdx.x;
     const long long total = static_cast<long long>(B) * G * G * 20;
-    if (idx >= total) return;
-    const int kv = idx % 20;
-    const long long row = idx / 20;
-    const int ox = row % G, oy = (row / G) % G, b = row / (static_cast<long long>(G) * G);
-    float f[8];
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+        const int kv = idx % 20;
+        const long long row = idx / 20;
+        const int ox = row % G, oy = (row / G) % G, b = row / (static_cast<long long>(G) * G);
+        float f[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int k = kv * 8 + i;
-        float val = 0.f;
-        if (k < 147) {
-            const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
-            const int iy = oy * 4 + ky - 3, ix = ox * 4 + kx - 3;
-            if (iy >= 0 && iy < S && ix >= 0 && ix < S)
-                val = __ldg(x + ((static_cast<size_t>(b) * 3 + c) * S + iy) * S + ix);
+        for (int i = 0; i < 8; ++i) {
+            const int k = kv * 8 + i;
+            float val = 0.f;
+            if (k < 147) {
+                const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
+                const int iy = oy * 4 + ky - 3, ix = ox * 4 + kx - 3;
+                if (iy >= 0 && iy < S && ix >= 0 && ix < S)
+                    val = __ldg(x + ((static_cast<size_t>(b) * 3 + c) * S + iy) * S + ix);
+            }
+            f[i] = val;
         }
-        f[i] = val;
+        reinterpret_cast<uint4*>(cols)[idx] = pack8(f);
     }
-    reinterpret_cast<uint4*>(cols)[idx] = pack8(f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -107,25 +119,25 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) maxpool_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H,
                                                       int W, int C4) {
     const int Ho = H >> 1, Wo = W >> 1;
-    const long long idx = blockIdx.x * 256ll + threadIdx.x;
     const long long total = static_cast<long long>(B) * Ho * Wo * C4;
-    if (idx >= total) return;
-    const int c = idx % C4;
-    const long long p = idx / C4;
-    const int ox = p % Wo, oy = (p / Wo) % Ho, b = p / (static_cast<long long>(Wo) * Ho);
-    const size_t base = ((static_cast<size_t>(b) * H + 2 * oy) * W + 2 * ox) * C4 + c;
-    const float4 a = x[base], bb = x[base + C4], cc = x[base + static_cast<size_t>(W) * C4],
-                 d = x[base + static_cast<size_t>(W) * C4 + C4];
-    y[idx] = make_float4(fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)), fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y)),
-                         fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)), fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w)));
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
+        const int c = idx % C4;
+        const long long p = idx / C4;
+        const int ox = p % Wo, oy = (p / Wo) % Ho, b = p / (static_cast<long long>(Wo) * Ho);
+        const size_t base = ((static_cast<size_t>(b) * H + 2 * oy) * W + 2 * ox) * C4 + c;
+        const float4 a = x[base], bb = x[base + C4], cc = x[base + static_cast<size_t>(W) * C4],
+                     d = x[base + static_cast<size_t>(W) * C4 + C4];
+        y[idx] = make_float4(fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)), fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y)),
+                             fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)), fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w)));
+    }
 }
 
 // fp32 -> bf16 cast, 8 elements per thread.
 __global__ void __launch_bounds__(256) cast_kernel(const float4* __restrict__ x, uint4* __restrict__ y, long long n8) {
-    const long long idx = blockIdx.x * 256ll + threadIdx.x;
-    if (idx >= n8) return;
-    const float4 a = x[2 * idx], b = x[2 * idx + 1];
-    y[idx] = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+    for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < n8; idx += gridDim.x * 256ll) {
+        const float4 a = x[2 * idx], b = x[2 * idx + 1];
+        y[idx] = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -149,35 +161,40 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, int out) {
 }
 
 // out[b,y,x,:] = concat(bilinear(src0)[C0], bilinear(src1)[C1]) in bf16 NHWC; src1 may be absent (C1 = 0).
-// One thread per (pixel, 8 channels).
+// One block per output row (b, oy): the vertical interpolation coefficients are block constants and the threads
+// sweep (ox, 8-channel vector) with coalesced 16-byte stores; neighbouring threads share source lines in L1.
 __global__ void __launch_bounds__(256)
 upcat_kernel(const uint4* __restrict__ s0, int h0, int w0, int c0v, const uint4* __restrict__ s1, int h1, int w1,
-             int c1v, uint4* __restrict__ out, int B, int Ho, int Wo) {
+             int c1v, uint4* __restrict__ out, int Ho, int Wo) {
     const int cv = c0v + c1v;
-    const long long idx = blockIdx.x * 256ll + threadIdx.x;
-    const long long total = static_cast<long long>(B) * Ho * Wo * cv;
-    if (idx >= total) return;
-    const int c = idx % cv;
-    const long long p = idx / cv;
-    const int ox = p % Wo, oy = (p / Wo) % Ho, b = p / (static_cast<long long>(Wo) * Ho);
-    const uint4* src;
-    int h, w, ncv, cc;
-    if (c < c0v) {
-        src = s0; h = h0; w = w0; ncv = c0v; cc = c;
-    } else {
-        src = s1; h = h1; w = w1; ncv = c1v; cc = c - c0v;
-    }
-    const Lerp ly = lerp_coord(oy, h, Ho), lx = lerp_coord(ox, w, Wo);
-    const size_t img = static_cast<size_t>(b) * h * w;
-    float a[8], bq[8], cq[8], d[8], r[8];
-    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i0) * ncv + cc), a);
-    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i1) * ncv + cc), bq);
-    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i0) * ncv + cc), cq);
-    unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i1) * ncv + cc), d);
+    const int oy = blockIdx.x, b = blockIdx.y;
+    const Lerp ly0 = lerp_coord(oy, h0, Ho);
+    const Lerp ly1 = c1v > 0 ? lerp_coord(oy, h1, Ho) : ly0;
+    uint4* orow = out + (static_cast<size_t>(b) * Ho + oy) * Wo * cv;
+    const int total = Wo * cv;
+    for (int t = threadIdx.x; t < total; t += 256) {
+        const int ox = t / cv;
+        const int c = t - ox * cv;
+        const uint4* src;
+        int h, w, ncv, cc;
+        Lerp ly;
+        if (c < c0v) {
+            src = s0; h = h0; w = w0; ncv = c0v; cc = c; ly = ly0;
+        } else {
+            src = s1; h = h1; w = w1; ncv = c1v; cc = c - c0v; ly = ly1;
+        }
+        const Lerp lx = lerp_coord(ox, w, Wo);
+        const size_t img = static_cast<size_t>(b) * h * w;
+        float a[8], bq[8], cq[8], d[8], r[8];
+        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i0) * ncv + cc), a);
+        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i1) * ncv + cc), bq);
+        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i0) * ncv + cc), cq);
+        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i1) * ncv + cc), d);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        r[i] = ly.w0 * (lx.w0 * a[i] + lx.w1 * bq[i]) + ly.w1 * (lx.w0 * cq[i] + lx.w1 * d[i]);
-    out[idx] = pack8(r);
+        for (int i = 0; i < 8; ++i)
+            r[i] = ly.w0 * (lx.w0 * a[i] + lx.w1 * bq[i]) + ly.w1 * (lx.w0 * cq[i] + lx.w1 * d[i]);
+        orow[t] = pack8(r);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -424,6 +441,12 @@ mask_stats_kernel(const float4* __restrict__ logits, const uchar4* __restrict__ 
 inline unsigned blocks_for(long long total, int per_block = 256) {
     return static_cast<unsigned>((total + per_block - 1) / per_block);
 }
+// grid-stride kernels: enough blocks to fill the machine several times over, far fewer than one per 256 elements
+inline unsigned capped_blocks(long long total) {
+    const long long want = (total + 255) / 256;
+    const long long cap = static_cast<long long>(sm_count()) * 16;
+    return static_cast<unsigned>(want < cap ? want : cap);
+}
 
 }  // namespace
 }  // namespace spg
@@ -433,8 +456,26 @@ using namespace spg;
 extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
                                       float eps, spg_stream_t stream) {
     SPG_CHECK_ARG(x && gamma && beta && y, "null pointer");
-    SPG_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= kLnMaxVec * 128, "LayerNorm needs C %% 4 == 0 and C <= 1152 (C=%d)", C);
-    layernorm_kernel<<<(M + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, static_cast<uint16_t*>(y), M, C, eps);
+    SPG_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= kLnMaxC, "LayerNorm needs C %% 4 == 0 and C <= 1152 (C=%d)", C);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint16_t* yo = static_cast<uint16_t*>(y);
+    // rows per warp so that one block (8 warps) streams roughly 64 KB+ and the grid stays far below the block-launch rate
+    if (C <= 256) {
+        const int rpw = 8;  // 8 * 2 rows per warp
+        const int rows_per_block = 8 * rpw * 2;
+        layernorm_kernel<16, 4><<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+    } else {
+        // register footprint follows the row length (float4 per lane): 3 for C <= 384, 5 for C <= 640, else 9
+        const int rpw = 4;
+        const int rows_per_block = 8 * rpw;
+        const unsigned grid = (M + rows_per_block - 1) / rows_per_block;
+        if (C <= 384)
+            layernorm_kernel<32, 3><<<grid, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+        else if (C <= 640)
+            layernorm_kernel<32, 5><<<grid, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+        else
+            layernorm_kernel<32, 9><<<grid, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+    }
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -443,7 +484,7 @@ extern "C" int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_
     SPG_CHECK_ARG(x && cols, "null pointer");
     SPG_CHECK_ARG(B > 0 && S > 0 && S % 4 == 0, "bad image size S=%d", S);
     const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * 20;
-    patchify_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint16_t*>(cols), B, S);
+    patchify_kernel<<<capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint16_t*>(cols), B, S);
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -452,7 +493,7 @@ extern "C" int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W,
     SPG_CHECK_ARG(x && y, "null pointer");
     SPG_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool needs even H, W and C %% 4 == 0");
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 4);
-    maxpool_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    maxpool_kernel<<<capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), B, H, W, C / 4);
     SPG_LAUNCHED();
     return SPG_OK;
@@ -461,7 +502,7 @@ extern "C" int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W,
 extern "C" int spg_cast_f32_h16(const float* x, void* y, long long n, spg_stream_t stream) {
     SPG_CHECK_ARG(x && y, "null pointer");
     SPG_CHECK_ARG(n > 0 && n % 8 == 0, "cast needs n %% 8 == 0");
-    cast_kernel<<<blocks_for(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    cast_kernel<<<capped_blocks(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(x), static_cast<uint4*>(y), n / 8);
     SPG_LAUNCHED();
     return SPG_OK;
@@ -472,10 +513,9 @@ extern "C" int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0,
     SPG_CHECK_ARG(src0 && out, "null pointer");
     SPG_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0 && c0 > 0 && c1 >= 0, "channel counts must be multiples of 8");
     SPG_CHECK_ARG(c1 == 0 || src1 != nullptr, "src1 is NULL but c1 > 0");
-    const long long total = static_cast<long long>(B) * Ho * Wo * ((c0 + c1) / 8);
-    upcat_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    upcat_kernel<<<dim3(Ho, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(src0), h0, w0, c0 / 8, static_cast<const uint4*>(src1), h1, w1, c1 / 8,
-        static_cast<uint4*>(out), B, Ho, Wo);
+        static_cast<uint4*>(out), Ho, Wo);
     SPG_LAUNCHED();
     return SPG_OK;
 }
