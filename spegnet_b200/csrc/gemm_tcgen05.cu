@@ -21,6 +21,7 @@
 // {64 ch, tile_w, tile_h, 1 image} of the NHWC input at (x0+dx-1, y0+dy-1); the zero halo comes
 // from TMA out-of-bounds fill, so the same MMA / epilogue pipeline serves both modes.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.h"
@@ -53,6 +54,7 @@ struct GemmArgs {
     int block_n;
     int num_m_tiles, num_n_tiles, num_k_chunks;
     int stages;
+    int pair;        // launch as CTA pairs (cta_group::2): decided on the host, selects the kPair kernel instance
     int halo;        // conv only: one stage = a 130-pixel halo row of A + the 3 dx-tap weight tiles (A reuse x3)
     // conv mode
     int conv;
@@ -95,7 +97,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // Epilogue traits are compile-time constants for the combinations the model launches (the hot loop then
 // carries no flag tests); -1 selects the run-time value from GemmArgs (generic fallback instance).
-template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut>
+// kPair = 1: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  A pair owns a 256 x block_n
+// tile: each CTA TMA-loads its own 128 A rows and HALF of the weight tile, the leader (cluster rank 0) issues
+// M=256 MMAs that read both CTAs' smem and fill both CTAs' TMEM, every CTA runs the epilogue of its 128 rows.
+// Staging half of W per CTA shrinks the stage (28 KB instead of 40 KB at N=192): more stages in flight per
+// TMA round trip and 30 % less L2->smem traffic per FLOP.
+template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut, int kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -108,7 +115,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
-    const uint32_t b_stage_bytes = static_cast<uint32_t>(p.block_n) * 128u;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    // bytes of ONE weight tile held by this CTA (pair mode: half of the block_n rows)
+    const uint32_t b_stage_bytes = static_cast<uint32_t>(kPair ? p.block_n / 2 : p.block_n) * 128u;
     // halo mode: A stage = 130 pixels x 128 B (padded to 17 KB so stages stay 1 KB aligned) + three weight tiles
     const uint32_t a_stage_bytes = p.halo ? kHaloABytes : kAStageBytes;
     const uint32_t stage_bytes = a_stage_bytes + (p.halo ? 3u : 1u) * b_stage_bytes;
@@ -124,7 +134,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+    // work distribution: a "unit" is a CTA (1-CTA mode) or a CTA pair; its m-block is 128 or 256 rows
+    const int total_tiles = (kPair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
+    const int unit = kPair ? blockIdx.x >> 1 : blockIdx.x;
+    const int nunits = kPair ? gridDim.x >> 1 : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -137,18 +150,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(tmem_empty_bar(a), kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (both CTAs)
         }
         for (int ew = 0; ew < kEpiWarps; ++ew)
             for (int s = 0; s < kResSlots; ++s) mbar_init(res_bar(ew, s), 1);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, kTmemCols);
-        tmem_relinquish();
+        if (kPair) {
+            tmem_alloc_pair(tmem_slot, kTmemCols);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all();  // the peer's barriers / TMEM must exist before any remote arrive or 2-CTA MMA
+    else __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -159,9 +178,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             const int hw = p.H * p.W;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_blk = tile / p.num_n_tiles;
-                const int n_blk = tile - m_blk * p.num_n_tiles;
+            // pair mode: both CTAs load; all transaction bytes are signalled on the leader's full barrier
+            const uint32_t n_half = kPair ? rank * (p.block_n / 2) : 0u;  // this CTA's slice of the weight tile
+            for (int tile = unit; tile < total_tiles; tile += nunits) {
+                const int m_unit = tile / p.num_n_tiles;
+                const int n_blk = tile - m_unit * p.num_n_tiles;
+                const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;  // this CTA's 128-row block
                 int img = 0, y0 = 0, x0 = 0;
                 if (p.conv) {
                     const int m0 = m_blk * kBlockM;
@@ -178,29 +200,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         // k-chunk = (dy, 64-channel chunk): one 130-pixel halo row serves the taps dx = -1, 0, +1
                         const int dyi = kc / p.cin_chunks;
                         const int cc = kc - dyi * p.cin_chunks;
-                        mbar_arrive_expect_tx(full_bar(stage), 130u * 128u + 3u * b_stage_bytes);
-                        tma_load_4d(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 - 1, y0 + dyi - 1, img);
+                        const uint32_t bytes = 130u * 128u + 3u * b_stage_bytes;
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), kPair ? 2u * bytes : bytes);
+                        if (kPair) tma_load_4d_pair(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 - 1, y0 + dyi - 1, img);
+                        else tma_load_4d(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 - 1, y0 + dyi - 1, img);
 #pragma unroll
-                        for (int dxi = 0; dxi < 3; ++dxi)
-                            tma_load_2d(b_dst + dxi * b_stage_bytes, &tmap_b, full_bar(stage),
-                                        ((dyi * 3 + dxi) * p.cin_chunks + cc) * kBlockK, n_blk * p.block_n);
+                        for (int dxi = 0; dxi < 3; ++dxi) {
+                            const int kcol = ((dyi * 3 + dxi) * p.cin_chunks + cc) * kBlockK;
+                            const int nrow = n_blk * p.block_n + n_half;
+                            if (kPair) tma_load_2d_pair(b_dst + dxi * b_stage_bytes, &tmap_b, full_bar(stage), kcol, nrow);
+                            else tma_load_2d(b_dst + dxi * b_stage_bytes, &tmap_b, full_bar(stage), kcol, nrow);
+                        }
                         if (++stage == p.stages) {
                             stage = 0;
                             phase ^= 1u;
                         }
                         continue;
                     }
-                    mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), kPair ? 2u * stage_bytes : stage_bytes);
                     if (p.conv) {
                         const int tap = kc / p.cin_chunks;
                         const int cc = kc - tap * p.cin_chunks;
                         const int dy = tap / 3 - 1;
                         const int dx = tap - (tap / 3) * 3 - 1;
-                        tma_load_4d(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 + dx, y0 + dy, img);
+                        if (kPair) tma_load_4d_pair(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 + dx, y0 + dy, img);
+                        else tma_load_4d(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 + dx, y0 + dy, img);
                     } else {
-                        tma_load_2d(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
+                        if (kPair) tma_load_2d_pair(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
+                        else tma_load_2d(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
                     }
-                    tma_load_2d(b_dst, &tmap_b, full_bar(stage), kc * kBlockK, n_blk * p.block_n);
+                    if (kPair) tma_load_2d_pair(b_dst, &tmap_b, full_bar(stage), kc * kBlockK, n_blk * p.block_n + n_half);
+                    else tma_load_2d(b_dst, &tmap_b, full_bar(stage), kc * kBlockK, n_blk * p.block_n);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1u;
@@ -210,13 +240,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16_f32(kBlockM, p.block_n);
+        if (lane == 0 && leader) {
+            const uint32_t idesc = make_idesc_bf16_f32(kPair ? 2 * kBlockM : kBlockM, p.block_n);
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t accum) {
+                if (kPair) umma_bf16_ss_pair(d, a, b, idesc, accum);
+                else umma_bf16_ss(d, a, b, idesc, accum);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (kPair) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < total_tiles; tile += nunits) {
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kAccStageCols;
@@ -236,7 +274,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                                 const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                                umma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (kc | dxi | k) != 0);
+                                mma(d_tmem, a_desc + koff, b_desc + koff, (kc | dxi | k) != 0);
                             }
                         }
                     } else {
@@ -246,16 +284,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                             // advance 32 B (= 16 elements) along K inside the 128 B swizzle atom
                             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
-                            umma_bf16_ss(d_tmem, a_desc + koff, b_desc + koff, idesc, (kc | k) != 0);
+                            mma(d_tmem, a_desc + koff, b_desc + koff, (kc | k) != 0);
                         }
                     }
-                    umma_commit(empty_bar(stage));
+                    commit(empty_bar(stage));
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(tmem_full_bar(acc));
+                commit(tmem_full_bar(acc));
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -292,9 +330,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // and the slot / parity bookkeeping of the residual loads running two groups ahead
         int slot = 0;
         uint32_t res_parity = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_blk = tile / p.num_n_tiles;
-            const int n_blk = tile - m_blk * p.num_n_tiles;
+        // the accumulator stage is handed back on the LEADER's tmem_empty barrier (the leader issues the MMAs)
+        const uint32_t tmem_empty_remote0 = kPair ? mapa_shared(tmem_empty_bar(0), 0) : 0u;
+        for (int tile = unit; tile < total_tiles; tile += nunits) {
+            const int m_unit = tile / p.num_n_tiles;
+            const int n_blk = tile - m_unit * p.num_n_tiles;
+            const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;
             const int n0 = n_blk * p.block_n;
             const int row0 = m_blk * kBlockM + quarter * 32;  // first output row of this warp
             const int res_row0 = p.res_rows > 0 ? row0 % p.res_rows : row0;
@@ -421,7 +462,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // accumulator fully read: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            if (lane == 0) {
+                if (kPair) mbar_arrive_cluster(tmem_empty_remote0 + 8u * acc);
+                else mbar_arrive(tmem_empty_bar(acc));
+            }
             if (has_head) {
                 // combine the two column halves of the fused N->1 head through smem
                 if (half == 1) headp_s[row_in_tile] = head_acc;
@@ -436,8 +480,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+    if (kPair) {
+        cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers
+        if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+    }
 }
 
 int pick_block_n(int N) {
@@ -446,12 +495,27 @@ int pick_block_n(int N) {
     return 0;
 }
 
+// CTA pairs (cta_group::2).  Must be decided before the weight tensor map is encoded: in pair mode each CTA's
+// TMA box is half of the block_n weight rows.  Measured on B200 (tests/cuda/test_gemm.cu --perf, B=64 shapes):
+// pairs gain 3-9 % on wide tiles with a long reduction (N=2304 K=2304: 1236 -> 1347 TFLOP/s, conv N=128: 1147 ->
+// 1237) and lose 3-18 % on short reductions and on N=64 tiles, where the per-tile handshake across the two CTAs is
+// not amortised; so they are used for block_n >= 128 with >= 16 k-steps and enough tiles to fill every SM pair.
+void decide_pair(GemmArgs& a) {
+    static const int pair_env = [] { const char* e = getenv("SPG_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+    const int ksteps = a.num_k_chunks * (a.halo ? 3 : 1);
+    const bool fits = a.block_n % 32 == 0 && a.num_m_tiles * a.num_n_tiles >= 2 * sm_count();
+    a.pair = (pair_env == 2 && fits) || (pair_env == 1 && fits && a.block_n >= 128 && ksteps >= 16) ? 1 : 0;
+}
+
 struct EpiMaps {
     CUtensorMap out, res;
 };
 
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, cudaStream_t stream) {
-    const int stage_bytes = a.halo ? kHaloABytes + 3 * a.block_n * 128 : kAStageBytes + a.block_n * 128;
+    const int total_1cta = a.num_m_tiles * a.num_n_tiles;
+    const bool pair = a.pair != 0;
+    const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
+    const int stage_bytes = a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128;
     const int staging = a.has_out ? kEpiWarps * kResSlots * a.buf_bytes : 0;
     const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
     int stages = (kSmemBudget - fixed) / stage_bytes;
@@ -460,20 +524,42 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     if (stages < 2) stages = 2;
     a.stages = stages;
     const int smem = stages * stage_bytes + fixed;
-    const int total = a.num_m_tiles * a.num_n_tiles;
     const int sms = sm_count();
-    const int grid = total < sms ? total : sms;
+    int grid;
+    if (pair) {
+        const int units = ((a.num_m_tiles + 1) / 2) * a.num_n_tiles;
+        grid = 2 * (units < sms / 2 ? units : sms / 2);
+    } else {
+        grid = total_1cta < sms ? total_1cta : sms;
+    }
     const bool head = a.head_w != nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     // the combinations SPEGNet launches get a compile-time specialised epilogue; anything else runs the generic one
-#define SPG_LAUNCH(ACT, F32, RES, HEAD, OUT)                                                                       \
+#define SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, PAIR)                                                             \
     do {                                                                                                           \
-        auto kern = gemm_tcgen05_kernel<ACT, F32, RES, HEAD, OUT>;                                                 \
+        auto kern = gemm_tcgen05_kernel<ACT, F32, RES, HEAD, OUT, PAIR>;                                           \
         static bool attr_set = false;                                                                              \
         if (!attr_set) {                                                                                           \
             SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
             attr_set = true;                                                                                       \
         }                                                                                                          \
-        kern<<<grid, kThreads, smem, stream>>>(ta, tb, em.out, em.res, a);                                         \
+        SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, a));                                 \
+    } while (0)
+#define SPG_LAUNCH(ACT, F32, RES, HEAD, OUT)                     \
+    do {                                                         \
+        if (pair) SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 1);   \
+        else SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 0);        \
     } while (0)
     if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 0, 0, 0, 1);
     else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1);
@@ -484,6 +570,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     else if (a.act == SPG_ACT_RELU && !a.has_res && head && !a.has_out) SPG_LAUNCH(SPG_ACT_RELU, 0, 0, 1, 0);
     else SPG_LAUNCH(-1, -1, -1, -1, -1);
 #undef SPG_LAUNCH
+#undef SPG_LAUNCH_ONE
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;
@@ -551,9 +638,10 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.cin_chunks = 1;
     a.tile_w = 1;
     if (int rc = fill_epilogue(a, em, ep, M, N)) return rc;
+    decide_pair(a);
     CUtensorMap ta, tb;
     if (int rc = make_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(K) * 2, kBlockM)) return rc;
-    if (int rc = make_tmap_2d(&tb, W, N, K, static_cast<uint64_t>(K) * 2, a.block_n)) return rc;
+    if (int rc = make_tmap_2d(&tb, W, N, K, static_cast<uint64_t>(K) * 2, a.pair ? a.block_n / 2 : a.block_n)) return rc;
     return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
 }
 
@@ -587,8 +675,9 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     a.halo = (tile_h == 1 && a.block_n <= 128) ? 1 : 0;
     if (a.halo) a.num_k_chunks = 3 * a.cin_chunks;
     if (int rc = fill_epilogue(a, em, ep, a.M, Cout)) return rc;
+    decide_pair(a);
     CUtensorMap ta, tb;
     if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, tile_h, a.halo ? 130 : tile_w)) return rc;
-    if (int rc = make_tmap_2d(&tb, w, Cout, 9ull * Cin, 18ull * Cin, a.block_n)) return rc;
+    if (int rc = make_tmap_2d(&tb, w, Cout, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;
     return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
 }
