@@ -127,6 +127,14 @@ int spg_window_attention_h16(const void* qkv, void* out, int B, int H, int W, in
                               int q_pool, spg_stream_t stream);
 
 /*
+ * The tcgen05 / TMEM implementation of the same operation for window == 16 without query pooling (the 32 windowed
+ * stage-3 blocks of Hiera-L): S = Q K^T and O = P V as tcgen05.mma tiles with the softmax probabilities kept in
+ * TMEM.  spg_window_attention_h16 dispatches to it automatically; other geometries return SPG_ERR_UNSUPPORTED.
+ */
+int spg_window_attention_tc_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads, int window,
+                                int q_pool, spg_stream_t stream);
+
+/*
  * out[b,y,x,:] = concat(bilinear(src0 [B,h0,w0,c0]), bilinear(src1 [B,h1,w1,c1])) resized to Ho x Wo,
  * align_corners=False, bf16 NHWC; src1 may be NULL with c1 = 0.  Replaces F.interpolate + torch.cat in
  * DecoderBlock.forward (models/object_detection.py:219-227).  Channel counts % 8 == 0.

@@ -43,6 +43,7 @@ SIGNATURES = {
     "spg_maxpool2x2_f32": [_P, _P, _I, _I, _I, _I, _P],
     "spg_cast_f32_h16": [_P, _P, _LL, _P],
     "spg_window_attention_h16": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "spg_window_attention_tc_h16": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "spg_upsample_concat_h16": [_P, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _P],
     "spg_fusion_combine": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "spg_row_sums_h16": [_P, _P, _I, _I, _I, _I, _P],

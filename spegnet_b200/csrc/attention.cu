@@ -11,6 +11,7 @@
 // and the online softmax in registers.  Attention is 4.7 % of the model's FLOPs;
 // moving the two GEMMs of it to tcgen05 is listed as next work in DESIGN.md.
 #include <atomic>
+#include <cstdlib>
 
 #include "common.h"
 #include "half16.cuh"
@@ -349,10 +350,19 @@ __global__ void __launch_bounds__(128) tiny_attention_kernel(const AttnParams p)
 }  // namespace
 }  // namespace spg
 
+extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads,
+                                           int window, int q_pool, spg_stream_t stream);
+
 extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads,
                                          int window, int q_pool, spg_stream_t stream) {
     using namespace spg;
     SPG_CHECK_ARG(qkv && out, "null pointer");
+    {
+        // 16x16 windows without query pooling (32 of Hiera-L's 48 blocks) run on tcgen05 / TMEM (attention_tc.cu)
+        static const int tc_env = [] { const char* e = getenv("SPG_ATTN_TC"); return e ? atoi(e) : 1; }();
+        if (tc_env && window == 16 && !q_pool && H % 16 == 0 && W % 16 == 0 && D == heads * 72)
+            return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, stream);
+    }
     SPG_CHECK_ARG(heads > 0 && D == heads * kHd, "attention is specialised for head_dim 72 (D=%d heads=%d)", D, heads);
     int ws = window;
     if (ws == 0) {

@@ -1,0 +1,335 @@
+// tcgen05 / TMEM window attention for the stage-3 windowed blocks of Hiera-L (16x16 windows = 256 keys,
+// 256 queries, head_dim 72):  out = softmax(q k^T / sqrt(72)) v  per (image, window, head).
+//
+// One persistent CTA per SM loops over (window, head) work items; a work item is two 128-query tiles.
+//   warp 0      TMA producer: 5-D boxes {d, 1 head, 1 of q|k|v, 16 x, 8 y} of the qkv tensor viewed as
+//               [72, heads, 3, W, B*H].  The 72-wide head dim is split into a 64-element SWIZZLE_128B box and a
+//               16-element SWIZZLE_32B tail box whose elements 72..79 are out of bounds in dim 0 and therefore
+//               ZERO-FILLED by the TMA unit (free K padding to 80 = 5 UMMA k-steps).  Q/K are double-buffered
+//               across work items, V single-buffered (it is consumed last).
+//   warp 1      MMA issuer: S = Q K^T as 4 + 1 SS-MMAs (M=128, N=256) into TMEM; then O = P V as TS-MMAs with the
+//               fp16 probabilities read from TMEM as the A operand and V as an MN-major B operand (N = 64 dims main
+//               + N = 16 tail), 16 k-steps of 16 keys.
+//   warps 2..9  two softmax / epilogue warpgroups, one per query tile, thread == query row: two passes over the S row
+//               in TMEM (max, then exp2 / sum) with double-buffered tcgen05.ld, P written back to TMEM in place as
+//               packed 16-bit pairs (tcgen05.st), O read back, scaled by 1/sum and stored.  No shuffles: every
+//               reduction is along a thread's own row.
+// TMEM: one 256-column region per query tile.  S occupies [0,256); P overwrites the consumed S columns [0,128);
+// O accumulates in [128,208).  The MMA warp issues S0, S1, PV0, PV1 per work item, so the tensor pipe works on one
+// tile while the other tile's warpgroup is in its softmax / epilogue.
+#include <atomic>
+
+#include "common.h"
+#include "half16.cuh"
+#include "ptx.cuh"
+
+namespace spg {
+extern std::atomic<long long> g_launches;
+namespace {
+
+constexpr int kHd = 72;
+constexpr int kWs = 16;                 // window edge
+constexpr int kKeys = kWs * kWs;        // 256
+constexpr int kThreadsTc = 320;  // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9 softmax of query tile 0 / 1
+constexpr uint32_t kQMain = 128 * 128;  // one 128-query tile, dims 0..63   (SWIZZLE_128B rows of 128 B)
+constexpr uint32_t kQTail = 128 * 32;   // dims 64..79                      (SWIZZLE_32B rows of 32 B)
+constexpr uint32_t kKMain = kKeys * 128, kKTail = kKeys * 32;
+// shared memory map (bytes, all 1 KB aligned)
+constexpr uint32_t kOffK = 0;                         // per stage: K main | K tail | Q main x2 | Q tail x2
+constexpr uint32_t kOffKt = kOffK + kKMain;
+constexpr uint32_t kOffQ = kOffKt + kKTail;
+constexpr uint32_t kOffQt = kOffQ + 2 * kQMain;
+constexpr uint32_t kStageQK = kOffQt + 2 * kQTail;    // 81920
+constexpr uint32_t kOffV = 2 * kStageQK;              // V main | V tail (single buffer)
+constexpr uint32_t kOffVt = kOffV + kKMain;
+constexpr uint32_t kOffBar = kOffVt + kKTail;         // 204800
+constexpr uint32_t kSmemTc = kOffBar + 256 + 1024;    // + barriers + alignment slack
+
+struct AttnTcParams {
+    h16* out;  // [B*H*W, D]
+    int B, H, W, D, heads;
+    int nwx, nwy;
+    int items;  // B * nwy * nwx * heads
+    float scale_log2e;
+};
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_tail,
+                    const AttnTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar = base + kOffBar;
+    // barriers: qk_full[2], qk_empty[2], v_full, v_empty, and per TMEM region r: s_full[r], p_full[r], o_full[r],
+    // region_free[r]
+    const uint32_t qk_full = bar, qk_empty = bar + 16, v_full = bar + 32, v_empty = bar + 40, s_full = bar + 48,
+                   p_full = bar + 64, o_full = bar + 80, region_free = bar + 96, tmem_slot = bar + 112;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_main);
+        tma_prefetch_desc(&tmap_tail);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(qk_full + 8 * s, 1);
+            mbar_init(qk_empty + 8 * s, 1);
+        }
+        mbar_init(v_full, 1);
+        mbar_init(v_empty, 1);
+        for (int r = 0; r < 2; ++r) {
+            mbar_init(s_full + 8 * r, 1);
+            mbar_init(p_full + 8 * r, 4);       // one arrive per softmax warp of the region's warpgroup
+            mbar_init(o_full + 8 * r, 1);
+            mbar_init(region_free + 8 * r, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int wins_per_img = p.nwx * p.nwy;
+    auto decode = [&](int item, int& head, int& y0, int& x0) {
+        head = item % p.heads;
+        const int win = item / p.heads;
+        const int b = win / wins_per_img;
+        const int wr = win - b * wins_per_img;
+        const int wy = wr / p.nwx, wx = wr - wy * p.nwx;
+        y0 = b * p.H + wy * kWs;  // row of the [B*H, W] token grid
+        x0 = wx * kWs;
+    };
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int n = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+                int head, y0, x0;
+                decode(item, head, y0, x0);
+                const int s = n & 1;
+                const uint32_t st = base + s * kStageQK;
+                const uint32_t fb = qk_full + 8 * s;
+                mbar_wait(qk_empty + 8 * s, ((n >> 1) & 1) ^ 1u);
+                mbar_arrive_expect_tx(fb, kStageQK);
+                for (int half = 0; half < 2; ++half) {  // 8 window rows = 128 tokens per box
+                    tma_load_5d(st + kOffK + half * (kKMain / 2), &tmap_main, fb, 0, head, 1, x0, y0 + 8 * half);
+                    tma_load_5d(st + kOffKt + half * (kKTail / 2), &tmap_tail, fb, 64, head, 1, x0, y0 + 8 * half);
+                    tma_load_5d(st + kOffQ + half * kQMain, &tmap_main, fb, 0, head, 0, x0, y0 + 8 * half);
+                    tma_load_5d(st + kOffQt + half * kQTail, &tmap_tail, fb, 64, head, 0, x0, y0 + 8 * half);
+                }
+                mbar_wait(v_empty, (n & 1) ^ 1u);
+                mbar_arrive_expect_tx(v_full, kKMain + kKTail);
+                for (int half = 0; half < 2; ++half) {
+                    tma_load_5d(base + kOffV + half * (kKMain / 2), &tmap_main, v_full, 0, head, 2, x0, y0 + 8 * half);
+                    tma_load_5d(base + kOffVt + half * (kKTail / 2), &tmap_tail, v_full, 64, head, 2, x0, y0 + 8 * half);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+#ifdef SPG_FP16
+            constexpr uint32_t kFmt = 0u;
+#else
+            constexpr uint32_t kFmt = 1u;
+#endif
+            constexpr uint32_t kIdescBase = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc_s = kIdescBase | ((256u >> 3) << 17);                      // K-major A and B
+            constexpr uint32_t idesc_pv64 = kIdescBase | (1u << 16) | ((64u >> 3) << 17);       // B MN-major
+            constexpr uint32_t idesc_pv16 = kIdescBase | (1u << 16) | ((16u >> 3) << 17);
+            // Event-driven issue: each TMEM region runs its own state machine (need S -> need PV -> next item) and the
+            // single MMA thread polls both with non-blocking barrier probes, issuing whichever step has its inputs
+            // ready.  A fixed issue order with blocking waits would hold one region's ready step behind the other
+            // region's barrier (measured: the softmax warps then idle ~40 % of the time on s_full / o_full).
+            auto issue_s = [&](int n, int r) {
+                const uint32_t st = base + (n & 1) * kStageQK;
+                tc_fence_after();
+                const uint32_t d = tmem_base + 256u * r;
+                const uint32_t qm = st + kOffQ + r * kQMain, qt = st + kOffQt + r * kQTail;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(d, make_smem_desc(qm + 32u * k, 2, 1024, 16),
+                                 make_smem_desc(st + kOffK + 32u * k, 2, 1024, 16), idesc_s, k != 0);
+                // dims 64..79 from the 32B-swizzled tails (72..79 are TMA zero fill)
+                umma_bf16_ss(d, make_smem_desc(qt, 6, 256, 16), make_smem_desc(st + kOffKt, 6, 256, 16), idesc_s, 1);
+                umma_commit(s_full + 8 * r);
+            };
+            auto issue_pv = [&](int r) {
+                tc_fence_after();
+                const uint32_t d = tmem_base + 256u * r;
+#pragma unroll 4
+                for (int k = 0; k < kKeys / 16; ++k) {
+                    const uint32_t a_tmem = d + 8u * k;  // 16 keys = 8 packed fp16-pair columns of P
+                    umma_ts(d + 128, a_tmem, make_smem_desc(base + kOffV + 2048u * k, 2, 1024, 16), idesc_pv64, k != 0);
+                    umma_ts(d + 192, a_tmem, make_smem_desc(base + kOffVt + 512u * k, 6, 256, 16), idesc_pv16, k != 0);
+                }
+                umma_commit(o_full + 8 * r);
+            };
+            const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+            int item_of[2] = {0, 0};      // next work item (CTA-local index) of each region
+            int need_pv[2] = {0, 0};      // 0: S not issued yet for item_of[r]; 1: S issued, PV pending
+            int s_count[2] = {0, 0};      // S steps issued per Q/K stage (both regions -> stage can be released)
+            int pv_count = 0;             // PV steps issued for the current V buffer
+            uint32_t spins = 0;
+            while (item_of[0] < my_items || item_of[1] < my_items) {
+                bool progressed = false;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int n = item_of[r];
+                    if (n >= my_items) continue;
+                    if (!need_pv[r]) {
+                        if (mbar_test(qk_full + 8 * (n & 1), (n >> 1) & 1) && mbar_test(region_free + 8 * r, (n & 1) ^ 1u)) {
+                            issue_s(n, r);
+                            if (++s_count[n & 1] == 2) {
+                                s_count[n & 1] = 0;
+                                umma_commit(qk_empty + 8 * (n & 1));  // Q / K of item n consumed by both tiles
+                            }
+                            need_pv[r] = 1;
+                            progressed = true;
+                        }
+                    } else {
+                        if (mbar_test(v_full, n & 1) && mbar_test(p_full + 8 * r, n & 1)) {
+                            issue_pv(r);
+                            if (++pv_count == 2) {
+                                pv_count = 0;
+                                umma_commit(v_empty);  // V of item n consumed by both tiles
+                            }
+                            need_pv[r] = 0;
+                            item_of[r] = n + 1;
+                            progressed = true;
+                        }
+                    }
+                }
+                if (progressed) {
+                    spins = 0;
+                } else if (++spins > (1u << 26)) {
+                    printf("spg: attention_tc MMA issuer stuck block=%d items=(%d,%d)\n", (int)blockIdx.x, item_of[0], item_of[1]);
+                    __trap();
+                }
+            }
+        }
+    } else {
+        // ============ softmax + epilogue: warps 2..5 own query tile 0, warps 6..9 query tile 1; thread == query row
+        const int r = (warp - 2) >> 2;        // query tile / TMEM region of this warpgroup
+        const int quarter = warp & 3;         // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;  // query row inside the 128-row tile
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u * r;
+        int n = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+            int head, y0, x0;
+            decode(item, head, y0, x0);
+            const uint32_t par = n & 1;
+            mbar_wait(s_full + 8 * r, par);
+            tc_fence_after();
+            uint32_t ra[32], rb[32];
+            // ---- pass 1: row maximum (32-column TMEM loads, double-buffered against the reductions)
+            float mx = -INFINITY;
+            tmem_ld32(lane_addr, ra);
+#pragma unroll 1
+            for (int c = 0; c < kKeys / 32; c += 2) {
+                tmem_ld_wait();
+                tmem_ld32(lane_addr + 32 * (c + 1), rb);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
+                tmem_ld_wait();
+                if (c + 2 < kKeys / 32) tmem_ld32(lane_addr + 32 * (c + 2), ra);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
+            }
+            const float m = mx * p.scale_log2e;
+            // ---- pass 2: p = 2^(s * scale - m), row sum, pack to 16 bit, write back over the consumed columns
+            float sum0 = 0.f, sum1 = 0.f;
+            auto exp_pack_store = [&](const uint32_t (&raw)[32], int c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0, p1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2e, -m)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2e, -m)));
+                    sum0 += p0;
+                    sum1 += p1;
+                    pk[i] = pack2(p0, p1);
+                }
+                tmem_st16(lane_addr + 16 * c, pk);
+            };
+            tmem_ld32(lane_addr, ra);
+#pragma unroll 1
+            for (int c = 0; c < kKeys / 32; c += 2) {
+                tmem_ld_wait();
+                tmem_ld32(lane_addr + 32 * (c + 1), rb);
+                exp_pack_store(ra, c);
+                tmem_ld_wait();
+                if (c + 2 < kKeys / 32) tmem_ld32(lane_addr + 32 * (c + 2), ra);
+                exp_pack_store(rb, c + 1);
+            }
+            const float sum = sum0 + sum1;
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full + 8 * r);
+            // ---- epilogue: O / sum -> out[token, head*72 .. +72)
+            const int q = r * 128 + row;
+            const long long tok = (static_cast<long long>(y0) + (q >> 4)) * p.W + x0 + (q & 15);
+            uint4* dst = reinterpret_cast<uint4*>(p.out + tok * p.D + head * kHd);
+            mbar_wait(o_full + 8 * r, par);
+            tc_fence_after();
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                uint32_t raw[16];
+                tmem_ld16(lane_addr + 128 + 16 * c, raw);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * inv;
+                dst[2 * c] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                if (c < 4)  // dims 72..79 of the last chunk are padding
+                    dst[2 * c + 1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]),
+                                                pack2(v[14], v[15]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(region_free + 8 * r);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+}  // namespace spg
+
+// tcgen05 path of spg_window_attention_h16 for window == 16 without query pooling (the 32 windowed stage-3 blocks).
+// Returns SPG_ERR_UNSUPPORTED for any other geometry; the caller then uses the generic kernel.
+extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads,
+                                           int window, int q_pool, spg_stream_t stream) {
+    using namespace spg;
+    SPG_CHECK_ARG(qkv && out, "null pointer");
+    if (window != kWs || q_pool || H % kWs || W % kWs || D != heads * kHd)
+        return fail(SPG_ERR_UNSUPPORTED, "tcgen05 attention covers 16x16 windows without query pooling");
+    AttnTcParams p{};
+    p.out = static_cast<h16*>(out);
+    p.B = B; p.H = H; p.W = W; p.D = D; p.heads = heads;
+    p.nwx = W / kWs; p.nwy = H / kWs;
+    p.items = B * p.nwx * p.nwy * heads;
+    p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
+    CUtensorMap tmain, ttail;
+    if (int rc = make_tmap_qkv_5d(&tmain, qkv, static_cast<uint64_t>(B) * H, W, heads, 64, kWs, 8, 128)) return rc;
+    if (int rc = make_tmap_qkv_5d(&ttail, qkv, static_cast<uint64_t>(B) * H, W, heads, 16, kWs, 8, 32)) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
+        attr_set = true;
+    }
+    const int grid = p.items < sm_count() ? p.items : sm_count();
+    attention_tc_kernel<<<grid, kThreadsTc, kSmemTc, static_cast<cudaStream_t>(stream)>>>(tmain, ttail, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    SPG_CHECK_LAUNCH();
+    return SPG_OK;
+}

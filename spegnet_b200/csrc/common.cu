@@ -119,6 +119,16 @@ int make_tmap_qkv_window(CUtensorMap* out, const void* base, uint64_t B, uint64_
     return encode(out, base, 4, dims, strides, box, -1, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
+int make_tmap_qkv_5d(CUtensorMap* out, const void* base, uint64_t BH, uint64_t W, uint64_t heads, uint32_t box_d,
+                     uint32_t box_w, uint32_t box_h, int swizzle_bytes) {
+    const uint64_t D = heads * 72;
+    cuuint64_t dims[5] = {72, heads, 3, W, BH};
+    cuuint64_t strides[4] = {72 * 2, D * 2, 3 * D * 2, W * 3 * D * 2};
+    cuuint32_t box[5] = {box_d, 1, 1, box_w, box_h};
+    return encode(out, base, 5, dims, strides, box, -1,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
 }  // namespace spg
 
 extern "C" int spg_version(void) { return 100; /* 0.1.0 */ }

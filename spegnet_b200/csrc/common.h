@@ -51,6 +51,13 @@ int make_tmap_epilogue(CUtensorMap* out, const void* base, uint64_t rows, uint64
 int make_tmap_qkv_window(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t ld,
                          uint32_t box_c, uint32_t box_w, uint32_t box_h);
 
+// qkv [B*H*W, 3*heads*72] viewed as the 5-D tensor [72 (head dim), heads, 3 (q|k|v), W, B*H]: a box
+// {box_d, 1, 1, box_w, box_h} is one head's slice of a window's tokens.  Because dim 0 has extent 72, a box that
+// starts at d = 64 with box_d = 16 gets dims 72..79 ZERO-FILLED by the TMA unit: the zero padding of the head
+// dimension to a multiple of the UMMA K step costs nothing.  swizzle_bytes = 128 (box_d = 64) or 32 (box_d = 16).
+int make_tmap_qkv_5d(CUtensorMap* out, const void* base, uint64_t BH, uint64_t W, uint64_t heads, uint32_t box_d,
+                     uint32_t box_w, uint32_t box_h, int swizzle_bytes);
+
 int sm_count();
 
 }  // namespace spg
