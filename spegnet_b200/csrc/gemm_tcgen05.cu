@@ -75,24 +75,23 @@ struct GemmArgs {
     float* head_out;
 };
 
-// Exact-erf GELU, 0.5 x (1 + erf(x / sqrt 2)), with a single-branch erf:
-//   erf(t) = 1 - 2^(t q(t)),  q = degree-5 minimax fit of log2(erfc(t)) / t on [0, 4],  t = min(|z|, 4)
-// max |erf error| 3.1e-7, max |GELU error| 4.8e-7 over all x when evaluated in fp32 (fit + check:
-// DESIGN.md "Numerics"); libdevice erff costs ~4x the issue slots because both of its branches are predicated.
+// Exact-erf GELU without libdevice erff (which costs ~4x the issue slots because both of its branches are
+// predicated).  With Phi the normal CDF, gelu(x) = x Phi(x) = max(x, 0) - |x| (1 - Phi(|x|)) and
+//   1 - Phi(t) = erfc(t / sqrt 2) / 2 = 2^(t q(t) - 1),   q = degree-5 minimax fit of log2(erfc(t / sqrt 2)) / t on
+// [0, 5.65], t = min(|x|, 5.65) (beyond it the term is < 1e-8 |x|).  10 FMA-pipe instructions + one MUFU.EX2;
+// max |error| 3.1e-7 over all x when evaluated in fp32 (fit + check: DESIGN.md "Numerics").
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float z = x * 0.70710678118654752440f;
-    const float t = fminf(fabsf(z), 4.0f);
-    float q = 0.00014203718455974013f;
-    q = fmaf(q, t, -0.0036641715560108423f);
-    q = fmaf(q, t, 0.03089582547545433f);
-    q = fmaf(q, t, -0.14969903230667114f);
-    q = fmaf(q, t, -0.9181656241416931f);
-    q = fmaf(q, t, -1.6279250383377075f);
+    const float ax = fabsf(x);
+    const float t = fminf(ax, 5.65f);
+    float q = 2.992223744513467e-05f;
+    q = fmaf(q, t, -0.0007398609886877239f);
+    q = fmaf(q, t, 0.007977429777383804f);
+    q = fmaf(q, t, -0.0532381497323513f);
+    q = fmaf(q, t, -0.45891571044921875f);
+    q = fmaf(q, t, -1.1511471271514893f);
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t * q));
-    const float erf_z = copysignf(1.0f - e, z);
-    const float hx = 0.5f * x;
-    return fmaf(hx, erf_z, hx);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(t, q, -1.0f)));
+    return fmaf(-ax, e, fmaxf(x, 0.f));
 }
 
 // Epilogue traits are compile-time constants for the combinations the model launches (the hot loop then
@@ -305,10 +304,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int half = ewarp >> 2;     // which half of the chunks
         const int etid = threadIdx.x - 64;
         const int row_in_tile = quarter * 32 + lane;
-        const int chunks = p.block_n >> 4;
-        const int c_begin = half == 0 ? 0 : (chunks + 1) >> 1;
-        const int c_end = half == 0 ? (chunks + 1) >> 1 : chunks;
-        const int n_my = c_end - c_begin;
         float* bias_s = reinterpret_cast<float*>(smem_raw + (scratch_addr - raw_addr));
         float* headw_s = bias_s + 2 * 256;
         float* headp_s = headw_s + 256;
@@ -337,10 +332,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n_blk = tile - m_unit * p.num_n_tiles;
             const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;
             const int n0 = n_blk * p.block_n;
+            // ragged last n-tile (N not a multiple of block_n): only the valid 16-column chunks are processed; the
+            // MMA still runs block_n wide on TMA zero-filled weight rows
+            const int chunks = min(p.block_n, p.N - n0) >> 4;
+            const int c_begin = half == 0 ? 0 : (chunks + 1) >> 1;
+            const int c_end = half == 0 ? (chunks + 1) >> 1 : chunks;
+            const int n_my = c_end - c_begin;
             const int row0 = m_blk * kBlockM + quarter * 32;  // first output row of this warp
             const int res_row0 = p.res_rows > 0 ? row0 % p.res_rows : row0;
             float* bs = bias_s + buf * 256;
-            if (etid < p.block_n) bs[etid] = p.bias != nullptr ? __ldg(p.bias + n0 + etid) : 0.f;
+            if (etid < p.block_n) bs[etid] = (p.bias != nullptr && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
 
             auto issue_res_load = [&](int sl, int c) {  // lane 0 only; c = first chunk of the group
                 const uint32_t bar = res_bar(ewarp, sl);
@@ -489,7 +490,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
 }
 
+// Tile width.  256-wide tiles run the tensor pipe ~15 % faster than 192-wide ones (measured 1347 vs 1150 TFLOP/s at
+// long K), so when N is not a multiple of 256 but the padding of a ragged last tile costs <= 12 % (N = 1728, 3456,
+// 1152: 3.7 / 3.7 / 11 %) the launch uses 256-wide tiles with a ragged tail; otherwise the largest divisor of N.
 int pick_block_n(int N) {
+    static const int ragged_env = [] { const char* e = getenv("SPG_GEMM_RAGGED"); return e ? atoi(e) : 1; }();
+    if (ragged_env && N > 256 && N % 256 != 0 && N % 64 == 0) {
+        const int padded = (N + 255) / 256 * 256;
+        if ((padded - N) * 100 <= 12 * N) return 256;
+    }
     for (int bn = 256; bn >= 16; bn -= 16)
         if (N % bn == 0) return bn;
     return 0;
@@ -504,7 +513,10 @@ void decide_pair(GemmArgs& a) {
     static const int pair_env = [] { const char* e = getenv("SPG_GEMM_PAIR"); return e ? atoi(e) : 1; }();
     const int ksteps = a.num_k_chunks * (a.halo ? 3 : 1);
     const bool fits = a.block_n % 32 == 0 && a.num_m_tiles * a.num_n_tiles >= 2 * sm_count();
-    a.pair = (pair_env == 2 && fits) || (pair_env == 1 && fits && a.block_n >= 128 && ksteps >= 16) ? 1 : 0;
+    // 256-wide tiles without a GELU epilogue also gain at K = 576 (QKV: 999 -> 1079 TFLOP/s); with GELU the
+    // epilogue is the longer phase and the cross-CTA handshake only adds to it (935 -> 926)
+    const bool wide_short = a.block_n == 256 && ksteps >= 8 && a.act != SPG_ACT_GELU && !a.has_res;
+    a.pair = (pair_env == 2 && fits) || (pair_env == 1 && fits && ((a.block_n >= 128 && ksteps >= 16) || wide_short)) ? 1 : 0;
 }
 
 struct EpiMaps {
@@ -600,6 +612,7 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
     a.out_f32 = ep->out_dtype == SPG_F32;
     // two chunks per staging buffer when each warp's half of the tile is a whole number of pairs
     a.group = (a.block_n % 64 == 0 && !a.has_res) ? 2 : 1;  // with a residual: 2 KB buffers -> one more mainloop stage
+
     a.row_bytes = a.group * 16 * (a.out_f32 ? 4 : 2);
     a.buf_bytes = 32 * a.row_bytes;
     a.piece_shift = a.row_bytes == 128 ? 0 : (a.row_bytes == 64 ? 1 : 2);
@@ -631,7 +644,7 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.N = N;
     a.block_n = pick_block_n(N);
     a.num_m_tiles = (M + kBlockM - 1) / kBlockM;
-    a.num_n_tiles = N / a.block_n;
+    a.num_n_tiles = (N + a.block_n - 1) / a.block_n;
     a.num_k_chunks = (K + kBlockK - 1) / kBlockK;
     a.conv = 0;
     a.H = a.W = 1;
