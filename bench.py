@@ -27,6 +27,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GFLOP_PER_IMAGE = {512: 610.98, 1024: 2530.89}  # algorithmic, reference formulation
+# DRAM traffic of one launch of the dominant kernel from an `ncu --set full` capture (profiles/
+# r01_gemm_qkv_ncu_full_summary.txt): the stage-3 QKV GEMM at batch 64 (M=65536, N=1728, K=576),
+# dram__bytes_read.sum 77.6 MB (algorithmic 77.5 MB: every operand byte is read exactly once) +
+# dram__bytes_write.sum 173.9 MB (algorithmic 226.5 MB; the remainder is still in the 126 MB L2 at kernel end).
+NCU_TRAFFIC = {"bytes_per_launch": 77_608_192 + 173_853_952, "launch": "stage-3 QKV GEMM, M=65536 N=1728 K=576",
+               "algorithmic_bytes": 65536 * 576 * 2 + 1728 * 576 * 2 + 65536 * 1728 * 2,
+               "source": "profiles/r01_gemm_qkv_ncu_full_summary.txt"}
 FALLBACK_PEAKS = {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
 CFG = {"encoder": {"config_path": "configs/sam2.1/sam2.1_hiera_l.yaml",
                    "checkpoint_path": "./checkpoints/sam2.1_hiera_large.pt", "variant": "large"}}
@@ -344,7 +351,9 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all Linear / 1x1 / 3x3-conv launches)",
                      "achieved": round(achieved_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": round(achieved_tf / peak_tf, 4), "traffic": None, "peak_source": f"{peak_src} sustained bf16",
+                     "frac": round(achieved_tf / peak_tf, 4),
+                     "traffic": NCU_TRAFFIC["bytes_per_launch"] if (B == 64 and S == 512) else None,
+                     "traffic_detail": NCU_TRAFFIC, "peak_source": f"{peak_src} sustained bf16",
                      "launches_per_step": n_gemm // max(args.steps, 1), "kernel_ms_per_step": round(gemm_ms / args.steps, 3),
                      "share_of_step": round(gemm_ms / elapsed_ms, 4)},
         "model_roofline": {"gflop_per_image": gflop_img, "achieved_tflops_per_gpu": round(model_tf, 1),
