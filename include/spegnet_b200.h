@@ -190,6 +190,27 @@ int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, con
 int spg_mask_stats_u8(const float* logits, const unsigned char* gt, unsigned char* mask, unsigned* stats, int B,
                       int HW, int double_sigmoid, spg_stream_t stream);
 
+/*
+ * The five camouflaged-object scores of the reference's metric wrapper, per image, on the GPU in fp64:
+ * replaces MetricsProcessor._process_single_sample (utils/metrics.py:142-167: py_sod_metrics Smeasure,
+ * WeightedFmeasure, MAE, Emeasure["adp"], Fmeasure["curve"].mean()) and the device->host copy + process pool
+ * around it (utils/metrics.py:224-231).  Inputs are the uint8 pairs that wrapper builds (:209-220): pred = uint8
+ * mask (e.g. from spg_mask_stats_u8), gt = uint8 with foreground > 128, both [B,H,W] contiguous.
+ *
+ * spg_sod_gt_prepare_u8: ground truth only (cache it per dataset): nearest[b,y,x] = y'*W + x' of the nearest
+ *   foreground pixel (-1 when the image has none), bit-identical to scipy.ndimage.distance_transform_edt(
+ *   return_indices=True) including its choice among equidistant pixels, and gt_stats[b][4] = {#fg, sum of fg
+ *   rows, sum of fg columns, 0} (the S-measure centroid).
+ * spg_sod_scores_u8: scores[b][5] = {S-alpha, weighted F-beta, MAE, adaptive E-phi, mean F-beta} as fp64.
+ * Both need a workspace of spg_sod_workspace_bytes(B,H,W) bytes (contents are scratch).
+ */
+size_t spg_sod_workspace_bytes(int B, int H, int W);
+int spg_sod_gt_prepare_u8(const unsigned char* gt, int B, int H, int W, int* nearest, unsigned long long* gt_stats,
+                          void* workspace, size_t ws_bytes, spg_stream_t stream);
+int spg_sod_scores_u8(const unsigned char* pred, const unsigned char* gt, const int* nearest,
+                      const unsigned long long* gt_stats, int B, int H, int W, double* scores, void* workspace,
+                      size_t ws_bytes, spg_stream_t stream);
+
 /* bf16 NHWC [B,HW,C] -> fp32 NCHW [B,C,HW] (materialises `features` entries of the output dict on demand). */
 int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream);
 

@@ -39,15 +39,22 @@ constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 constexpr int kHaloABytes = 17 * 1024;  // 130 halo pixels x 128 B = 16640 B, padded to a 1 KB multiple
-constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kEpiWarps = 8;
+// warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 (two per TMEM lane quarter) or 16 (four per quarter).  The epilogue
+// is issue-bound (ncu: 16 instructions per output element with GELU, 60 % issue utilisation with two warps per
+// scheduler), so the variants without a residual run 16 warps to hide each other's fixed-latency stalls.
+constexpr int kMaxEpiWarps = 16;
 constexpr int kTmemCols = 512;
 constexpr int kAccStageCols = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kBarBytes = 512;                                 // pipeline barriers + residual barriers
-constexpr int kEpiScratch = (2 * 256 + 256 + 128) * 4;          // bias[2][256], head weights[256], head partials[128]
-constexpr int kResSlots = 3;                                    // staging ring depth when a residual is streamed in
+constexpr int kBarBytes = 1024;                                // pipeline barriers + residual barriers
+constexpr int kEpiScratch = (2 * 256 + 256 + 3 * 128) * 4;      // bias[2][256], head weights[256], head partials[3][128]
+#ifndef SPG_RES_SLOTS
+#define SPG_RES_SLOTS 3
+#endif
+// staging ring depth; with a residual, kResSlots - 1 residual groups are in flight per epilogue warp
+constexpr int kResSlots = SPG_RES_SLOTS;
+static_assert(kResSlots >= 3 && kResSlots <= 8, "staging ring depth");
 
 struct GemmArgs {
     int M, N;
@@ -66,6 +73,7 @@ struct GemmArgs {
     int res_rows;
     int has_out;
     int out_f32;
+    int epi_warps;    // 8 or 16 epilogue warps (selects the kernel instance)
     int group;        // 16-column chunks per staging buffer / TMA op (1 or 2)
     int row_bytes;    // bytes per staging row = group * 16 * sizeof(out)   (32 / 64 / 128)
     int buf_bytes;    // 32 * row_bytes
@@ -77,20 +85,21 @@ struct GemmArgs {
 
 // Exact-erf GELU without libdevice erff (which costs ~4x the issue slots because both of its branches are
 // predicated).  With Phi the normal CDF, gelu(x) = x Phi(x) = max(x, 0) - |x| (1 - Phi(|x|)) and
-//   1 - Phi(t) = erfc(t / sqrt 2) / 2 = 2^(t q(t) - 1),   q = degree-5 minimax fit of log2(erfc(t / sqrt 2)) / t on
-// [0, 5.65], t = min(|x|, 5.65) (beyond it the term is < 1e-8 |x|).  10 FMA-pipe instructions + one MUFU.EX2;
-// max |error| 3.1e-7 over all x when evaluated in fp32 (fit + check: DESIGN.md "Numerics").
+//   1 - Phi(t) = erfc(t / sqrt 2) / 2 = 2^P(t),   P = degree-4 fit of log2(erfc(t / sqrt 2)) - 1 on [0, 5.65] that
+// minimises the error of the PRODUCT t 2^P(t) (weighted minimax), t = min(|x|, 5.65) (beyond it the term is
+// < 1e-8 |x|).  5 FMA + 2 FMNMX + one MUFU.EX2 per element; max |error| 6.2e-6 over all x when evaluated in fp32,
+// 20x below the rounding of the fp16 result at |gelu| ~ 0.25 (the degree-6 form it replaces reached 3.1e-7 for two more
+// FMAs per element in an epilogue that is bound by instruction issue; fit + check: DESIGN.md "Numerics").
 __device__ __forceinline__ float gelu_erf(float x) {
     const float ax = fabsf(x);
     const float t = fminf(ax, 5.65f);
-    float q = 2.992223744513467e-05f;
-    q = fmaf(q, t, -0.0007398609886877239f);
-    q = fmaf(q, t, 0.007977429777383804f);
-    q = fmaf(q, t, -0.0532381497323513f);
-    q = fmaf(q, t, -0.45891571044921875f);
-    q = fmaf(q, t, -1.1511471271514893f);
+    float q = 0.0038662622682750225f;
+    q = fmaf(q, t, -0.044079262763261795f);
+    q = fmaf(q, t, -0.46801483631134033f);
+    q = fmaf(q, t, -1.1473722457885742f);
+    q = fmaf(q, t, -1.0004795789718628f);
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(t, q, -1.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
     return fmaf(-ax, e, fmaxf(x, 0.f));
 }
 
@@ -101,8 +110,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // M=256 MMAs that read both CTAs' smem and fill both CTAs' TMEM, every CTA runs the epilogue of its 128 rows.
 // Staging half of W per CTA shrinks the stage (28 KB instead of 40 KB at N=192): more stages in flight per
 // TMA round trip and 30 % less L2->smem traffic per FLOP.
-template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut, int kPair>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut, int kPair, int kEpiWarps>
+__global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                     const GemmArgs p) {
@@ -299,9 +308,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
     } else {
         // ===================== epilogue (warps 2..9) =====================
-        const int ewarp = warp - 2;      // 0..7
+        constexpr int kParts = kEpiWarps / 4;  // warps sharing one TMEM lane quarter split the tile's columns
+        constexpr int kEpiThreads = 32 * kEpiWarps;
+        const int ewarp = warp - 2;      // 0..kEpiWarps-1
         const int quarter = warp & 3;    // TMEM lane quarter this warp may access
-        const int half = ewarp >> 2;     // which half of the chunks
+        const int part = ewarp >> 2;     // which slice of the chunks
         const int etid = threadIdx.x - 64;
         const int row_in_tile = quarter * 32 + lane;
         float* bias_s = reinterpret_cast<float*>(smem_raw + (scratch_addr - raw_addr));
@@ -335,8 +346,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // ragged last n-tile (N not a multiple of block_n): only the valid 16-column chunks are processed; the
             // MMA still runs block_n wide on TMA zero-filled weight rows
             const int chunks = min(p.block_n, p.N - n0) >> 4;
-            const int c_begin = half == 0 ? 0 : (chunks + 1) >> 1;
-            const int c_end = half == 0 ? (chunks + 1) >> 1 : chunks;
+            // balanced split in units of one staging group (a group is never shared between warps); the first part
+            // takes the remainder of an odd chunk count
+            const int units = (chunks + p.group - 1) / p.group;
+            const int c_begin = part == 0 ? 0 : min(chunks, p.group * ((units * part + kParts - 1) / kParts));
+            const int c_end = part == kParts - 1 ? chunks : min(chunks, p.group * ((units * (part + 1) + kParts - 1) / kParts));
             const int n_my = c_end - c_begin;
             const int row0 = m_blk * kBlockM + quarter * 32;  // first output row of this warp
             const int res_row0 = p.res_rows > 0 ? row0 % p.res_rows : row0;
@@ -348,13 +362,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 mbar_arrive_expect_tx(bar, p.buf_bytes);
                 tma_load_2d(my_staging + sl * p.buf_bytes, &tmap_res, bar, n0 + c * 16, res_row0);
             };
-            const int slot1 = slot == kResSlots - 1 ? 0 : slot + 1;
             if (has_res && lane == 0) {
-                tma_store_wait_read<1>();  // these two slots were last read by the stores 3 and 2 groups ago
-                issue_res_load(slot, c_begin);
-                if (n_my > p.group) issue_res_load(slot1, c_begin + p.group);
+                // the kResSlots - 1 slots after the last published one: every store but the most recent has read them
+                tma_store_wait_read<1>();
+                int sl = slot;
+#pragma unroll
+                for (int i = 0; i < kResSlots - 1; ++i) {
+                    if (i * p.group < n_my) issue_res_load(sl, c_begin + i * p.group);
+                    sl = sl == kResSlots - 1 ? 0 : sl + 1;
+                }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // bias staged (double-buffered across tiles)
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // bias staged (double-buffered across tiles)
 
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
@@ -439,10 +457,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             tma_store_commit();
                         }
                     }
-                    if (has_res && lane == 0 && c + 1 + p.group < c_end) {
-                        // the group two ahead reuses the slot of the previous group: its store must be done reading
+                    if (has_res && lane == 0 && c + 1 + (kResSlots - 2) * p.group < c_end) {
+                        // the group kResSlots - 1 ahead reuses the slot of the previous group: its store must be done reading
                         tma_store_wait_read<1>();
-                        issue_res_load(slot == 0 ? kResSlots - 1 : slot - 1, c + 1 + p.group);
+                        issue_res_load(slot == 0 ? kResSlots - 1 : slot - 1, c + 1 + (kResSlots - 2) * p.group);
                     }
                     slot = slot == kResSlots - 1 ? 0 : slot + 1;
                 }
@@ -468,10 +486,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 else mbar_arrive(tmem_empty_bar(acc));
             }
             if (has_head) {
-                // combine the two column halves of the fused N->1 head through smem
-                if (half == 1) headp_s[row_in_tile] = head_acc;
-                asm volatile("bar.sync 2, 256;" ::: "memory");
-                if (half == 0 && row_ok) p.head_out[row] = head_acc + headp_s[row_in_tile] + p.head_b;
+                // combine the column slices of the fused N->1 head through smem
+                if (part > 0) headp_s[(part - 1) * 128 + row_in_tile] = head_acc;
+                asm volatile("bar.sync 2, %0;" ::"n"(kEpiThreads) : "memory");
+                if (part == 0 && row_ok) {
+#pragma unroll
+                    for (int k = 1; k < kParts; ++k) head_acc += headp_s[(k - 1) * 128 + row_in_tile];
+                    p.head_out[row] = head_acc + p.head_b;
+                }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
@@ -528,7 +550,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     const bool pair = a.pair != 0;
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
     const int stage_bytes = a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128;
-    const int staging = a.has_out ? kEpiWarps * kResSlots * a.buf_bytes : 0;
+    const int staging = a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0;
     const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -547,7 +569,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     const bool head = a.head_w != nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(64 + 32 * a.epi_warps);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -558,9 +580,9 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // the combinations SPEGNet launches get a compile-time specialised epilogue; anything else runs the generic one
-#define SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, PAIR)                                                             \
+#define SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, PAIR, EW)                                                         \
     do {                                                                                                           \
-        auto kern = gemm_tcgen05_kernel<ACT, F32, RES, HEAD, OUT, PAIR>;                                           \
+        auto kern = gemm_tcgen05_kernel<ACT, F32, RES, HEAD, OUT, PAIR, EW>;                                       \
         static bool attr_set = false;                                                                              \
         if (!attr_set) {                                                                                           \
             SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
@@ -568,19 +590,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
         }                                                                                                          \
         SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, a));                                 \
     } while (0)
-#define SPG_LAUNCH(ACT, F32, RES, HEAD, OUT)                     \
-    do {                                                         \
-        if (pair) SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 1);   \
-        else SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 0);        \
+#define SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, EW)                     \
+    do {                                                             \
+        if (pair) SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 1, EW);   \
+        else SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 0, EW);        \
     } while (0)
-    if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 0, 0, 0, 1);
-    else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1);
-    else if (a.act == SPG_ACT_NONE && a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 0, 0, 1);
-    else if (a.act == SPG_ACT_GELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_GELU, 0, 0, 0, 1);
-    else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_RELU, 0, 0, 0, 1);
-    else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && head && a.has_out) SPG_LAUNCH(SPG_ACT_RELU, 0, 0, 1, 1);
-    else if (a.act == SPG_ACT_RELU && !a.has_res && head && !a.has_out) SPG_LAUNCH(SPG_ACT_RELU, 0, 0, 1, 0);
-    else SPG_LAUNCH(-1, -1, -1, -1, -1);
+    // 16-warp epilogues exist for the specialised instances without a residual (fill_epilogue picks epi_warps)
+#define SPG_LAUNCH_EW(ACT, F32, RES, HEAD, OUT)                      \
+    do {                                                             \
+        if (a.epi_warps == 16) SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, 16); \
+        else SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, 8);                \
+    } while (0)
+    if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_NONE, 0, 0, 0, 1);
+    else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1, 8);
+    else if (a.act == SPG_ACT_NONE && a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 0, 0, 1, 8);
+    else if (a.act == SPG_ACT_GELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_GELU, 0, 0, 0, 1);
+    else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 0, 1);
+    else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 1, 1);
+    else if (a.act == SPG_ACT_RELU && !a.has_res && head && !a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 1, 0);
+    else SPG_LAUNCH(-1, -1, -1, -1, -1, 8);
+#undef SPG_LAUNCH_EW
 #undef SPG_LAUNCH
 #undef SPG_LAUNCH_ONE
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -610,8 +639,15 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
     a.res_rows = ep->res_rows;
     a.has_out = ep->out != nullptr;
     a.out_f32 = ep->out_dtype == SPG_F32;
-    // two chunks per staging buffer when each warp's half of the tile is a whole number of pairs
-    a.group = (a.block_n % 64 == 0 && !a.has_res) ? 2 : 1;  // with a residual: 2 KB buffers -> one more mainloop stage
+    // 16 epilogue warps for the specialised h16-output instances (SPG_GEMM_EW=8 forces the 8-warp kernels)
+    static const int ew_env = [] { const char* e = getenv("SPG_GEMM_EW"); return e ? atoi(e) : 16; }();
+    const bool ew16_instance = !a.has_res && !a.out_f32 &&
+                               ((ep->head_w == nullptr && a.has_out) || (a.act == SPG_ACT_RELU && ep->head_w != nullptr));
+    a.epi_warps = (ew_env == 16 && ew16_instance) ? 16 : 8;
+    // two chunks per staging buffer / TMA op when every warp's slice of the tile is a whole number of pairs
+    // (with a residual: 2 KB buffers -> one more mainloop stage)
+    // 16 warps: one chunk per buffer keeps the staging ring at 48 KB (16 x 3 x 1 KB), i.e. the same number of mainloop stages
+    a.group = (a.epi_warps == 8 && a.block_n % 64 == 0 && !a.has_res) ? 2 : 1;
 
     a.row_bytes = a.group * 16 * (a.out_f32 ? 4 : 2);
     a.buf_bytes = 32 * a.row_bytes;

@@ -210,3 +210,37 @@ def mae_from_stats(stats: torch.Tensor, n_pixels: int) -> torch.Tensor:
     norm = ((sbg - lo * nbg) + (hi * nfg - sfg)) / torch.where(span > 0, span, torch.ones_like(span))
     flat = sbg / 255.0 + (nfg - sfg / 255.0)
     return torch.where(span > 0, norm, flat) / n_pixels
+
+
+def sod_gt_prepare(gt_u8: torch.Tensor):
+    """gt_u8 [B,H,W] uint8 (foreground > 128) -> (nearest int32 [B,H,W], gt_stats int64 [B,4]).  Ground truth only:
+    cache the result per dataset.  See spg_sod_gt_prepare_u8."""
+    B, H, W = gt_u8.shape
+    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    nbytes = int(lib.spg_sod_workspace_bytes(B, H, W))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=gt_u8.device)
+    nearest = torch.empty(B, H, W, dtype=torch.int32, device=gt_u8.device)
+    stats = torch.empty(B, 4, dtype=torch.int64, device=gt_u8.device)
+    rc = lib.spg_sod_gt_prepare_u8(_ptr(gt_u8, torch.uint8, "gt"), B, H, W, _ptr(nearest, torch.int32, "nearest"),
+                                   _ptr(stats, torch.int64, "gt_stats"), _ptr(ws, torch.uint8, "workspace"), nbytes,
+                                   _stream())
+    _lib.check(rc, "spg_sod_gt_prepare_u8", dn)
+    return nearest, stats
+
+
+def sod_scores(pred_u8: torch.Tensor, gt_u8: torch.Tensor, nearest: torch.Tensor, gt_stats: torch.Tensor) -> torch.Tensor:
+    """uint8 masks + prepared ground truth -> fp64 [B,5] = (S-alpha, weighted F, MAE, adaptive E, mean F) per image
+    (the per-sample scores of utils/metrics.py:161-167).  See spg_sod_scores_u8."""
+    B, H, W = gt_u8.shape
+    if tuple(pred_u8.shape) != (B, H, W):
+        raise ValueError(f"pred {tuple(pred_u8.shape)} and gt {tuple(gt_u8.shape)} differ")
+    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    nbytes = int(lib.spg_sod_workspace_bytes(B, H, W))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=gt_u8.device)
+    scores = torch.empty(B, 5, dtype=torch.float64, device=gt_u8.device)
+    rc = lib.spg_sod_scores_u8(_ptr(pred_u8, torch.uint8, "pred"), _ptr(gt_u8, torch.uint8, "gt"),
+                               _ptr(nearest, torch.int32, "nearest"), _ptr(gt_stats, torch.int64, "gt_stats"), B, H, W,
+                               _ptr(scores, torch.float64, "scores"), _ptr(ws, torch.uint8, "workspace"), nbytes,
+                               _stream())
+    _lib.check(rc, "spg_sod_scores_u8", dn)
+    return scores

@@ -283,6 +283,16 @@ int main(int argc, char** argv) {
         return 98;
     }
     printf("libspegnet_b200 version %d\n", spg_version());
+    // ad-hoc timing of one GEMM shape (ncu / tuning):  --shape M N K act(0|1|2) res(0|1) f32(0|1)
+    for (int i = 1; i + 6 < argc; ++i) {
+        if (!strcmp(argv[i], "--shape")) {
+            g_perf = true;
+            g_check = false;
+            case_gemm(atoi(argv[i + 1]), atoi(argv[i + 2]), atoi(argv[i + 3]), atoi(argv[i + 4]), true, atoi(argv[i + 5]) != 0, 0,
+                      atoi(argv[i + 6]) != 0, false);
+            return g_fail;
+        }
+    }
     if (g_check) {
     // smallest possible: one tile, one k-chunk
     case_gemm(128, 64, 64, SPG_ACT_NONE, false, false, 0, true, false);

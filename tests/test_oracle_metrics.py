@@ -79,3 +79,79 @@ def test_aggregate_is_plain_mean():
     rows = [{"sm": 1.0, "wfm": 0.5, "mae": 0.1, "em": 0.9, "fm": 0.7}, {"sm": 0.0, "wfm": 0.5, "mae": 0.3, "em": 0.7, "fm": 0.1}]
     agg = M.aggregate(rows)
     assert agg == pytest.approx({"s_alpha": 0.5, "weighted_f": 0.5, "mae": 0.2, "e_phi": 0.8, "mean_f": 0.4})
+
+
+def _feature_transform_int(fg):
+    """Host restatement of the integer algorithm of csrc/metrics.cu (ft_columns_kernel + ft_rows_kernel): nearest
+    foreground pixel per pixel, with scipy's choice among equidistant candidates."""
+    H, W = fg.shape
+    fy = -np.ones((H, W), np.int64)
+    for x in range(W):
+        last = -1
+        for y in range(H):
+            if fg[y, x]:
+                last = y
+            fy[y, x] = last
+        nxt = -1
+        for y in range(H - 1, -1, -1):
+            if fg[y, x]:
+                nxt = y
+            up = fy[y, x]
+            if nxt >= 0 and (up < 0 or nxt - y < y - up):
+                fy[y, x] = nxt
+    out = -np.ones((H, W), np.int64)
+    for y in range(H):
+        g = []
+        for ii in range(W):
+            if fy[y, ii] < 0:
+                continue
+            wR = (fy[y, ii] - y) ** 2
+            while len(g) >= 2:
+                i1, i2 = g[-1], g[-2]
+                a, b = i1 - i2, ii - i1
+                c = a + b
+                uR, vR = (fy[y, i2] - y) ** 2, (fy[y, i1] - y) ** 2
+                if c * vR - b * uR - a * wR - a * b * c <= 0:
+                    break
+                g.pop()
+            g.append(ii)
+        if not g:
+            continue
+        l = 0
+        for ii in range(W):
+            d1 = (g[l] - ii) ** 2 + (fy[y, g[l]] - y) ** 2
+            while l < len(g) - 1:
+                d2 = (g[l + 1] - ii) ** 2 + (fy[y, g[l + 1]] - y) ** 2
+                if d1 <= d2:
+                    break
+                d1 = d2
+                l += 1
+            out[y, ii] = fy[y, g[l]] * W + g[l]
+    return out
+
+
+def test_integer_feature_transform_reproduces_scipy_including_ties():
+    """The GPU weighted-F pass reads the prediction error AT the nearest foreground pixel, so the choice among
+    equidistant pixels matters; the kernels' integer scan must make scipy's choice (pinned here on the host, and
+    bit-for-bit on the GPU in tests/test_gpu_metrics.py)."""
+    from scipy.ndimage import distance_transform_edt
+
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        H, W = (int(v) for v in rng.integers(5, 36, 2))
+        kind = trial % 4
+        if kind == 0:
+            fg = rng.random((H, W)) < 0.05
+        elif kind == 1:
+            fg = rng.random((H, W)) < 0.5
+        elif kind == 2:
+            yy, xx = np.mgrid[:H, :W]
+            fg = ((yy - H / 2) ** 2 / (H / 3) ** 2 + (xx - W / 2) ** 2 / (W / 4) ** 2) < 1
+        else:
+            fg = np.zeros((H, W), bool)
+            fg[rng.integers(0, H), rng.integers(0, W)] = True
+            fg[rng.integers(0, H), rng.integers(0, W)] = True
+        if not fg.any():
+            continue
+        _, idx = distance_transform_edt(~fg, return_indices=True)
+        assert np.array_equal(_feature_transform_int(fg), idx[0] * W + idx[1]), trial
