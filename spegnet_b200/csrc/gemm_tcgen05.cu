@@ -39,10 +39,11 @@ constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 constexpr int kHaloABytes = 17 * 1024;  // 130 halo pixels x 128 B = 16640 B, padded to a 1 KB multiple
-// warp 0 TMA, warp 1 MMA, warps 2.. epilogue: 8 (two per TMEM lane quarter) or 16 (four per quarter).  The epilogue
-// is issue-bound (ncu: 16 instructions per output element with GELU, 60 % issue utilisation with two warps per
-// scheduler), so the variants without a residual run 16 warps to hide each other's fixed-latency stalls.
-constexpr int kMaxEpiWarps = 16;
+// warp 0 TMA, warp 1 MMA, warps 2.. epilogue.  The kernel is written for 4 * k epilogue warps (k warps per TMEM lane
+// quarter splitting the tile's columns); every instance runs 8.  16 warps were measured on B200 and gain nothing
+// (fc1+GELU 963 vs 971 TFLOP/s, stage-1 fc1 470 vs 468 us): short-K shapes are bound by the TMA round trip of a
+// smem-limited ring, not by epilogue latency hiding.
+constexpr int kEpiWarpsDefault = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStageCols = 256;
 constexpr int kMaxStages = 8;
@@ -595,20 +596,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
         if (pair) SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 1, EW);   \
         else SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 0, EW);        \
     } while (0)
-    // 16-warp epilogues exist for the specialised instances without a residual (fill_epilogue picks epi_warps)
-#define SPG_LAUNCH_EW(ACT, F32, RES, HEAD, OUT)                      \
-    do {                                                             \
-        if (a.epi_warps == 16) SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, 16); \
-        else SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, 8);                \
-    } while (0)
+#define SPG_LAUNCH_EW(ACT, F32, RES, HEAD, OUT) SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, kEpiWarpsDefault)
     if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_NONE, 0, 0, 0, 1);
-    else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1, 8);
-    else if (a.act == SPG_ACT_NONE && a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 0, 0, 1, 8);
+    else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1, kEpiWarpsDefault);
+    else if (a.act == SPG_ACT_NONE && a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 0, 0, 1, kEpiWarpsDefault);
     else if (a.act == SPG_ACT_GELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_GELU, 0, 0, 0, 1);
     else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 0, 1);
     else if (a.act == SPG_ACT_RELU && !a.out_f32 && !a.has_res && head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 1, 1);
     else if (a.act == SPG_ACT_RELU && !a.has_res && head && !a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 1, 0);
-    else SPG_LAUNCH(-1, -1, -1, -1, -1, 8);
+    else SPG_LAUNCH(-1, -1, -1, -1, -1, kEpiWarpsDefault);
 #undef SPG_LAUNCH_EW
 #undef SPG_LAUNCH
 #undef SPG_LAUNCH_ONE
@@ -639,15 +635,10 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
     a.res_rows = ep->res_rows;
     a.has_out = ep->out != nullptr;
     a.out_f32 = ep->out_dtype == SPG_F32;
-    // 16 epilogue warps for the specialised h16-output instances (SPG_GEMM_EW=8 forces the 8-warp kernels)
-    static const int ew_env = [] { const char* e = getenv("SPG_GEMM_EW"); return e ? atoi(e) : 16; }();
-    const bool ew16_instance = !a.has_res && !a.out_f32 &&
-                               ((ep->head_w == nullptr && a.has_out) || (a.act == SPG_ACT_RELU && ep->head_w != nullptr));
-    a.epi_warps = (ew_env == 16 && ew16_instance) ? 16 : 8;
+    a.epi_warps = kEpiWarpsDefault;
     // two chunks per staging buffer / TMA op when every warp's slice of the tile is a whole number of pairs
     // (with a residual: 2 KB buffers -> one more mainloop stage)
-    // 16 warps: one chunk per buffer keeps the staging ring at 48 KB (16 x 3 x 1 KB), i.e. the same number of mainloop stages
-    a.group = (a.epi_warps == 8 && a.block_n % 64 == 0 && !a.has_res) ? 2 : 1;
+    a.group = (a.block_n % 64 == 0 && !a.has_res) ? 2 : 1;
 
     a.row_bytes = a.group * 16 * (a.out_f32 ? 4 : 2);
     a.buf_bytes = 32 * a.row_bytes;

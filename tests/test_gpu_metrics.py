@@ -157,3 +157,30 @@ def test_full_size_properties(ops):
     n2, s2 = ops.sod_gt_prepare(gt_u8[perm].contiguous())
     b = ops.sod_scores(pred[perm].contiguous(), gt_u8[perm].contiguous(), n2, s2)
     assert torch.equal(a[perm], b)
+
+
+def test_evaluate_dataset_matches_host_scoring_of_the_same_logits(ops, spread_sd):
+    """Evaluator path end to end (engine/evaluator.py:522-560): forward -> sigmoid -> MetricsProcessor (sigmoid * 255
+    -> byte again) -> five scores -> dataset means, all on the GPU, against the oracle scoring the same logits on the
+    host with the reference wrapper's recipe."""
+    from oracle.sod_metrics import aggregate, quantise_like_reference, score_pair
+    from spegnet_b200 import SPEGNet, evaluate
+
+    dev = torch.device("cuda", 0)
+    model = SPEGNet({"encoder": {"config_path": "", "checkpoint_path": "", "variant": "large"}})
+    model.load_state_dict(spread_sd)
+    model = model.to(dev).eval()
+    S, N = 256, 5
+    fn = evaluate.synthetic_batch_fn(S, dev)
+    got = evaluate.evaluate_dataset(model, N, 2, fn)  # batches of 2, 2, 1 (ragged tail)
+    rows = []
+    for i in range(N):
+        img, gt = fn([i])
+        with torch.no_grad():
+            logits = model(img)["predictions"][-1][0, 0].cpu()
+        q = quantise_like_reference(torch.sigmoid(logits).numpy())  # second sigmoid inside, utils/metrics.py:209
+        rows.append(score_pair(q, gt[0].cpu().numpy()))
+    want = aggregate(rows)
+    for k, v in want.items():
+        assert abs(got[k] - v) <= 1e-5, (k, got[k], v)
+    assert tuple(got["rows"].shape) == (N, 5)
