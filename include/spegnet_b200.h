@@ -94,6 +94,30 @@ int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, 
                      const spg_epilogue_t* ep, spg_stream_t stream);
 
 /*
+ * Bilinear x2 upsample (align_corners=False) FUSED into the 3x3 convolution that consumes it:
+ *   out[B, 2H, 2W, Cout] = relu(conv3x3_pad1(up2(x))[..., co] + bias)      x: NHWC bf16 [B,H,W,Cin]
+ * Replaces F.interpolate(x, size=2x) followed by conv1 + bn1 + relu of the last DecoderBlock (no edge branch:
+ * models/object_detection.py:219,230-232 with models/spegnet.py:187-191), without materialising the upsampled map.
+ * Both operators are linear, so each of the 4 output phases (row phase a, column phase b of the x2 grid) is a 3x3
+ * convolution on the LOW-resolution grid with its own folded weights: an implicit GEMM with N = 4*Cout (one 256-wide
+ * tcgen05 tile for Cout = 64 instead of four times as many 64-wide ones) and a pixel-shuffle TMA store.
+ *   w_phase [3][4*Cout][9*Cin] bf16: one weight set per ROW CLASS of the low-resolution pixel (0: first image row,
+ *       1: interior, 2: last row), n = (a*2 + b)*Cout + co, k = (dy*3 + dx)*Cin + ci.  The first / last row differ
+ *       because the bilinear clamp and the conv's zero padding meet there.
+ *   corr [2][B*H][4*Cout] fp32: pre-activation corrections of the first (side 0) / last (side 1) image COLUMN, the
+ *       same border effect along x: corr = spg_up2_border_gather_h16(x) @ delta_w^T via spg_linear_h16.
+ *   bias4 [4*Cout] fp32 (the folded BatchNorm shift repeated per phase).
+ * W % 128 == 0, Cin % 64 == 0, Cout % 32 == 0, Cout <= 64.  The host-side weight folding is spegnet_b200/model.py
+ * (`up2_phase_weights`), pinned against F.interpolate + F.conv2d in tests/test_host.py and tests/test_gpu_ops.py.
+ */
+int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const float* corr, int B, int H, int W, int Cin, int Cout,
+                        const float* bias4, void* out, spg_stream_t stream);
+
+/* Left operand of the border-column correction GEMM above: out [2][B*H][9*C] bf16,
+ * out[s][b*H+y][(cls*3+dy)*C + c] = x[b, y+dy-1, s ? W-1 : 0, c] in the block of y's row class, zero elsewhere. */
+int spg_up2_border_gather_h16(const void* x, void* out, int B, int H, int W, int C, spg_stream_t stream);
+
+/*
  * y[M,C] (bf16) = LayerNorm(x[M,C] (fp32 residual stream)) * gamma + beta, eps as given (1e-6 in Hiera).
  * Replaces blocks.{i}.norm1 / norm2 (HF:modeling_sam2.py:495,528).  C % 4 == 0, C <= 1152.
  */

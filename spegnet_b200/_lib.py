@@ -38,6 +38,8 @@ _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "spg_linear_h16": [_P, _P, _I, _I, _I, C.POINTER(Epilogue), _P],
     "spg_conv3x3_h16": [_P, _P, _I, _I, _I, _I, _I, C.POINTER(Epilogue), _P],
+    "spg_conv3x3_up2_h16": [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "spg_up2_border_gather_h16": [_P, _P, _I, _I, _I, _I, _P],
     "spg_layernorm_f32_h16": [_P, _P, _P, _P, _I, _I, _F, _P],
     "spg_patchify_7x7s4": [_P, _P, _I, _I, _P],
     "spg_maxpool2x2_f32": [_P, _P, _I, _I, _I, _I, _P],

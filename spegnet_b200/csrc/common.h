@@ -46,6 +46,11 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
 int make_tmap_epilogue(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, int elem_is_f32,
                        uint32_t box_cols);
 
+// Pixel-shuffle store map of the fused "bilinear x2 -> 3x3 conv" kernel: out [B, 2H, 2W, C] viewed as the 5-D tensor
+// [C, 2 (column phase), W, 2 (row phase), B*H]; a box {box_cols, 1, 32, 1, 1} is 32 low-resolution pixels of one
+// output phase -- in shared memory the same 32 x box_cols tile the 2-D epilogue map stores.
+int make_tmap_up2_out(CUtensorMap* out, const void* base, uint64_t BH, uint64_t W, uint64_t C, uint32_t box_cols);
+
 // qkv [B*H*W, ld] viewed as [B, H, W, ld]: box = {box_c channels, box_w, box_h, 1 image}, no swizzle
 // (dense rows of box_c elements in shared memory).  One box = the K or V tile of one attention window / head.
 int make_tmap_qkv_window(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t ld,

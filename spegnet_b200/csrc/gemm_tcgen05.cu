@@ -67,6 +67,13 @@ struct GemmArgs {
     // conv mode
     int conv;
     int H, W, cin_chunks, tile_w;
+    // fused bilinear x2 upsample (kUp2 instances): the conv runs on the LOW-resolution grid with 4 output phases stacked
+    // along N; w holds one [N, K] weight set per row class (top / interior / bottom image row), corr the pre-activation
+    // corrections of the first / last image column, the store is a pixel shuffle (see spg_conv3x3_up2_h16)
+    int up2;
+    int cout;            // channels per phase (N = 4 * cout)
+    int bh;              // B * H
+    const float* corr;   // [2][B*H][N] fp32
     // epilogue
     const float* bias;
     int act;
@@ -111,7 +118,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // M=256 MMAs that read both CTAs' smem and fill both CTAs' TMEM, every CTA runs the epilogue of its 128 rows.
 // Staging half of W per CTA shrinks the stage (28 KB instead of 40 KB at N=192): more stages in flight per
 // TMA round trip and 30 % less L2->smem traffic per FLOP.
-template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut, int kPair, int kEpiWarps>
+template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut, int kPair, int kEpiWarps, int kUp2 = 0>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -201,6 +208,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     y0 = rem / p.W;
                     x0 = rem - y0 * p.W;
                 }
+                // kUp2: the tile is part of one image row; rows 0 / H-1 use their own weight sets (stacked along N)
+                const int w_row0 = kUp2 ? (y0 == 0 ? 0 : (y0 == p.H - 1 ? 2 * p.N : p.N)) : 0;
                 for (int kc = 0; kc < p.num_k_chunks; ++kc) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t a_dst = tiles_addr + stage * stage_bytes;
@@ -216,7 +225,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int dxi = 0; dxi < 3; ++dxi) {
                             const int kcol = ((dyi * 3 + dxi) * p.cin_chunks + cc) * kBlockK;
-                            const int nrow = n_blk * p.block_n + n_half;
+                            const int nrow = w_row0 + n_blk * p.block_n + n_half;
                             if (kPair) tma_load_2d_pair(b_dst + dxi * b_stage_bytes, &tmap_b, full_bar(stage), kcol, nrow);
                             else tma_load_2d(b_dst + dxi * b_stage_bytes, &tmap_b, full_bar(stage), kcol, nrow);
                         }
@@ -238,8 +247,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         if (kPair) tma_load_2d_pair(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
                         else tma_load_2d(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
                     }
-                    if (kPair) tma_load_2d_pair(b_dst, &tmap_b, full_bar(stage), kc * kBlockK, n_blk * p.block_n + n_half);
-                    else tma_load_2d(b_dst, &tmap_b, full_bar(stage), kc * kBlockK, n_blk * p.block_n);
+                    if (kPair) tma_load_2d_pair(b_dst, &tmap_b, full_bar(stage), kc * kBlockK, w_row0 + n_blk * p.block_n + n_half);
+                    else tma_load_2d(b_dst, &tmap_b, full_bar(stage), kc * kBlockK, w_row0 + n_blk * p.block_n);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1u;
@@ -355,6 +364,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int n_my = c_end - c_begin;
             const int row0 = m_blk * kBlockM + quarter * 32;  // first output row of this warp
             const int res_row0 = p.res_rows > 0 ? row0 % p.res_rows : row0;
+            // kUp2: position of this warp's 32 low-resolution pixels, and the correction row of a border-column pixel
+            int up_img_row = 0, up_x = 0;
+            const float* corr_row = nullptr;
+            if (kUp2) {
+                const int hw = p.H * p.W;
+                const int img = row0 / hw;
+                const int rem = row0 - img * hw;
+                const int y = rem / p.W;
+                up_x = rem - y * p.W;
+                up_img_row = img * p.H + y;
+                const int x = up_x + lane;
+                if (x == 0) corr_row = p.corr + static_cast<size_t>(up_img_row) * p.N + n0;
+                else if (x == p.W - 1) corr_row = p.corr + (static_cast<size_t>(p.bh) + up_img_row) * p.N + n0;
+            }
             float* bs = bias_s + buf * 256;
             if (etid < p.block_n) bs[etid] = (p.bias != nullptr && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
 
@@ -407,6 +430,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
                     v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
                 }
+                if (kUp2 && corr_row != nullptr) {  // first / last image column: bilinear clamp + conv zero padding
+                    const float4* c4 = reinterpret_cast<const float4*>(corr_row + col);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 cc = __ldg(c4 + i);
+                        v[4 * i + 0] += cc.x;
+                        v[4 * i + 1] += cc.y;
+                        v[4 * i + 2] += cc.z;
+                        v[4 * i + 3] += cc.w;
+                    }
+                }
                 if (act == SPG_ACT_RELU) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -454,7 +488,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, row0);
+                            if (kUp2) {
+                                const int n = n0 + c_first * 16;
+                                const int phase = n / p.cout;  // (row phase, column phase) = (phase >> 1, phase & 1)
+                                tma_store_5d(&tmap_out, my_staging + slot * p.buf_bytes, n - phase * p.cout, phase & 1, up_x,
+                                             phase >> 1, up_img_row);
+                            } else {
+                                tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, row0);
+                            }
                             tma_store_commit();
                         }
                     }
@@ -591,13 +632,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
         }                                                                                                          \
         SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, a));                                 \
     } while (0)
+#define SPG_LAUNCH_ONE_UP2(PAIR)                                                                                   \
+    do {                                                                                                           \
+        auto kern = gemm_tcgen05_kernel<SPG_ACT_RELU, 0, 0, 0, 1, PAIR, kEpiWarpsDefault, 1>;                       \
+        static bool attr_set = false;                                                                              \
+        if (!attr_set) {                                                                                           \
+            SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
+            attr_set = true;                                                                                       \
+        }                                                                                                          \
+        SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, a));                                 \
+    } while (0)
 #define SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, EW)                     \
     do {                                                             \
         if (pair) SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 1, EW);   \
         else SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 0, EW);        \
     } while (0)
 #define SPG_LAUNCH_EW(ACT, F32, RES, HEAD, OUT) SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, kEpiWarpsDefault)
-    if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_NONE, 0, 0, 0, 1);
+    if (a.up2) {
+        if (pair) SPG_LAUNCH_ONE_UP2(1);
+        else SPG_LAUNCH_ONE_UP2(0);
+    } else if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_NONE, 0, 0, 0, 1);
     else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1, kEpiWarpsDefault);
     else if (a.act == SPG_ACT_NONE && a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 0, 0, 1, kEpiWarpsDefault);
     else if (a.act == SPG_ACT_GELU && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_GELU, 0, 0, 0, 1);
@@ -606,6 +660,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     else if (a.act == SPG_ACT_RELU && !a.has_res && head && !a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 1, 0);
     else SPG_LAUNCH(-1, -1, -1, -1, -1, kEpiWarpsDefault);
 #undef SPG_LAUNCH_EW
+#undef SPG_LAUNCH_ONE_UP2
 #undef SPG_LAUNCH
 #undef SPG_LAUNCH_ONE
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -719,5 +774,52 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     CUtensorMap ta, tb;
     if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, tile_h, a.halo ? 130 : tile_w)) return rc;
     if (int rc = make_tmap_2d(&tb, w, Cout, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;
+    return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const float* corr, int B, int H, int W, int Cin,
+                                   int Cout, const float* bias4, void* out, spg_stream_t stream) {
+    using namespace spg;
+    SPG_CHECK_ARG(x != nullptr && w_phase != nullptr && corr != nullptr && out != nullptr, "x / w_phase / corr / out is NULL");
+    SPG_CHECK_ARG(B > 0 && H >= 2 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
+    SPG_CHECK_ARG(Cin % kBlockK == 0, "Cin=%d must be a multiple of 64", Cin);
+    SPG_CHECK_ARG(Cout % 32 == 0 && 4 * Cout <= 256, "Cout=%d must be a multiple of 32 and <= 64 (4 phases in one 256-wide tile)", Cout);
+    SPG_CHECK_ARG(W % kBlockM == 0, "W=%d must be a multiple of 128 (a tile is 128 pixels of one low-resolution row)", W);
+    SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(corr) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias4) & 15) == 0,
+                  "corr / bias4 must be 16-byte aligned");
+    GemmArgs a{};
+    EpiMaps em;
+    a.M = B * H * W;
+    a.N = 4 * Cout;
+    a.block_n = a.N;
+    a.num_m_tiles = a.M / kBlockM;
+    a.num_n_tiles = 1;
+    a.cin_chunks = Cin / kBlockK;
+    a.num_k_chunks = 9 * a.cin_chunks;
+    a.conv = 1;
+    a.H = H;
+    a.W = W;
+    a.tile_w = kBlockM;
+    a.halo = 0;
+    a.up2 = 1;
+    a.cout = Cout;
+    a.bh = B * H;
+    a.corr = corr;
+    a.bias = bias4;
+    a.act = SPG_ACT_RELU;
+    a.has_out = 1;
+    a.epi_warps = kEpiWarpsDefault;
+    a.group = 2;  // 32 columns: never straddles a phase (Cout % 32 == 0)
+    a.row_bytes = 64;
+    a.buf_bytes = 32 * 64;
+    a.piece_shift = 1;
+    a.piece_mask = 3;
+    memset(&em, 0, sizeof(em));
+    if (int rc = make_tmap_up2_out(&em.out, out, static_cast<uint64_t>(B) * H, W, Cout, 32)) return rc;
+    decide_pair(a);
+    if (W % (2 * kBlockM) != 0) a.pair = 0;  // both CTAs of a pair must sit in the same image row (same weight set)
+    CUtensorMap ta, tb;
+    if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, 1, kBlockM)) return rc;
+    if (int rc = make_tmap_2d(&tb, w_phase, 3ull * a.N, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;
     return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
 }

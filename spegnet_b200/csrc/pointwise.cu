@@ -379,6 +379,31 @@ __global__ void __launch_bounds__(256) aspp_kernel(const AsppParams p) {
     p.y[pix * 16 + t] = pack8(o);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Operand of the border-column correction GEMM of the fused "bilinear x2 -> 3x3 conv" (spg_conv3x3_up2_h16):
+// for side s (0: column 0, 1: column W-1), image b, row y:   A[s][b*H + y][(cls*3 + dy)*C + c] = x[b, y+dy-1, col, c]
+// inside the block cls = row class of y (0 top, 1 interior, 2 bottom) and zero in the other two class blocks and
+// outside the image, so that ONE weight matrix [N, 9C] carries the three row-class variants.  8 channels / thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+up2_border_gather_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int C8) {
+    const long long total = 2ll * B * H * 9 * C8;
+    const long long idx = blockIdx.x * 256ll + threadIdx.x;
+    if (idx >= total) return;
+    const int c = idx % C8;
+    const int blk = (idx / C8) % 9;       // cls * 3 + dy
+    const long long r = idx / (9ll * C8);  // side * B*H + b*H + y
+    const int y = r % H;
+    const int b = (r / H) % B;
+    const int side = r / (static_cast<long long>(B) * H);
+    const int cls = y == 0 ? 0 : (y == H - 1 ? 2 : 1);
+    const int yy = y + blk % 3 - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (blk / 3 == cls && yy >= 0 && yy < H)
+        v = x[((static_cast<size_t>(b) * H + yy) * W + (side ? W - 1 : 0)) * C8 + c];
+    out[idx] = v;
+}
+
 // bf16 NHWC -> fp32 NCHW (for the lazily materialised `features` entries of the output dict).
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, int HW, int C, long long total) {
@@ -582,6 +607,16 @@ extern "C" int spg_mask_stats_u8(const float* logits, const unsigned char* gt, u
     mask_stats_kernel<<<dim3(per_img, B), 256, 0, st>>>(reinterpret_cast<const float4*>(logits),
                                                         reinterpret_cast<const uchar4*>(gt),
                                                         reinterpret_cast<uchar4*>(mask), stats, HW / 4, double_sigmoid);
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_up2_border_gather_h16(const void* x, void* out, int B, int H, int W, int C, spg_stream_t stream) {
+    SPG_CHECK_ARG(x && out, "null pointer");
+    SPG_CHECK_ARG(B > 0 && H >= 2 && W >= 2 && C % 8 == 0, "bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
+    const long long total = 2ll * B * H * 9 * (C / 8);
+    up2_border_gather_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), static_cast<uint4*>(out), B, H, W, C / 8);
     SPG_LAUNCHED();
     return SPG_OK;
 }

@@ -68,6 +68,42 @@ def _is_seq_bn(name: str) -> bool:
         name.startswith("context.branches.") and name.split(".")[3] == "1")
 
 
+def up2_operators(n: int = 8) -> torch.Tensor:
+    """R[cls, a, t, d]: coefficient of low-resolution sample i + d - 1 in the bilinear x2 (align_corners=False) value
+    at high-resolution position 2i + a + t - 1, for i in the first (cls 0) / an interior (1) / the last (2) row or
+    column; positions outside the upsampled grid (the conv's zero padding) and samples outside the input contribute
+    0.  Read off ATen's own operator (F.interpolate of unit impulses), so the clamp at the border is ATen's."""
+    U = F.interpolate(torch.eye(n, dtype=torch.float64)[None], scale_factor=2, mode="linear", align_corners=False)[0].t()
+    R = torch.zeros(3, 2, 3, 3, dtype=torch.float64)
+    for cls, i in enumerate((0, n // 2, n - 1)):
+        for a in range(2):
+            for t in range(3):
+                h = 2 * i + a + t - 1
+                for d in range(3):
+                    j = i + d - 1
+                    if 0 <= h < 2 * n and 0 <= j < n:
+                        R[cls, a, t, d] = U[h, j]
+    return R
+
+
+def up2_phase_weights(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fold `conv3x3(pad=1) o bilinear_x2` (models/object_detection.py:219,230) into convolutions on the low-resolution
+    grid.  w [Cout,Cin,3,3] -> (main [3*4*Cout, 9*Cin], delta_left [4*Cout, 9*Cin], delta_right [4*Cout, 9*Cin]):
+    main[cls*4*Cout + (a*2+b)*Cout + co, (dy*3+dx)*Cin + ci] for row class cls with interior column weights;
+    delta_side[(a*2+b)*Cout + co, (cls*3+dy)*Cin + ci] = what the first / last image column adds on top (it only involves
+    the border column itself).  See spg_conv3x3_up2_h16."""
+    R = up2_operators().to(w.device, torch.float64)
+    w64 = w.to(torch.float64)
+    Co, Ci = w.shape[:2]
+    main = torch.cat([torch.einsum("oiyx,ayd,bxe->abodei", w64, R[c], R[1]).reshape(4 * Co, 9 * Ci) for c in range(3)])
+    deltas = []
+    for side in (0, 2):
+        dcol = (R[side] - R[1])[:, :, 1]  # [b, tx]: the other two offsets are unchanged (asserted in tests)
+        deltas.append(torch.cat([torch.einsum("oiyx,ayd,bx->abodi", w64, R[c], dcol).reshape(4 * Co, 3 * Ci)
+                                 for c in range(3)], dim=1))
+    return main.to(w.dtype), deltas[0].to(w.dtype), deltas[1].to(w.dtype)
+
+
 class LazyFeatures(Mapping):
     """``outputs['features']``: the reference returns fp32 NCHW tensors that no call site reads
     (SURVEY.md 3.3).  The kernels keep them as bf16 NHWC; this mapping converts on first access."""
@@ -127,7 +163,10 @@ class _Workspace:
         self.u2 = e(B * 16 * h * h * 320, bf).view(B, 4 * h, 4 * h, 320)
         self.d2a = e(B * 16 * h * h * 128, bf).view(B, 4 * h, 4 * h, 128)
         self.d2 = e(B * 16 * h * h * 128, bf).view(B, 4 * h, 4 * h, 128)
-        self.u3 = e(B * 64 * h * h * 128, bf).view(B, 8 * h, 8 * h, 128)
+        # stage 3 runs the upsample fused into its first conv: border-column operand + corrections instead of a
+        # materialised [B, 8h, 8h, 128] map
+        self.bord = e(2 * B * 4 * h * 9 * 128, bf).view(2, B * 4 * h, 9 * 128)
+        self.corr = e(2 * B * 4 * h * 256, f32).view(2, B * 4 * h, 256)
         self.d3a = e(B * 64 * h * h * 64, bf).view(B, 8 * h, 8 * h, 64)
         self.pos: Optional[torch.Tensor] = None  # [G*G, 144] fp32, set by the model (input independent)
 
@@ -261,19 +300,27 @@ class SPEGNet(nn.Module):
         W["exp.w"] = (f32(sd["context.expand.0.weight"]).reshape(256, 128) * s[:, None]).to(bf).contiguous()
         W["exp.b"] = sh.contiguous()
 
-        def conv3(wkey: str, bkey: Optional[str], bnp: str, out: str):
+        def conv3(wkey: str, bkey: Optional[str], bnp: str, out: str, up2: bool = False):
             s, sh = bn_fold(bnp)
             w = f32(sd[wkey])  # [Cout, Cin, 3, 3]
-            w = (w * s[:, None, None, None]).permute(0, 2, 3, 1).reshape(w.shape[0], -1)  # [Cout, (ky,kx,ci)]
-            W[out + ".w"] = w.to(bf).contiguous()
-            W[out + ".b"] = (sh + (f32(sd[bkey]) * s if bkey else 0.0)).contiguous()
+            w = w * s[:, None, None, None]
+            bias = (sh + (f32(sd[bkey]) * s if bkey else 0.0)).contiguous()
+            if up2:  # the conv consumes a bilinear x2 upsample: fold it in (4 phases on the low-resolution grid)
+                main, dl, dr = up2_phase_weights(w)
+                W[out + ".wp"] = main.to(bf).contiguous()
+                W[out + ".dwl"] = dl.to(bf).contiguous()
+                W[out + ".dwr"] = dr.to(bf).contiguous()
+                W[out + ".bp"] = bias.repeat(4).contiguous()
+                return
+            W[out + ".w"] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(bf).contiguous()  # [Cout, (ky,kx,ci)]
+            W[out + ".b"] = bias
 
         conv3("edge_detector.conv1.weight", None, "edge_detector.bn1.", "edge")
         W["edge.hw"] = f32(sd["edge_detector.edge_conv.weight"]).reshape(-1)
         W["edge.hb"] = f32(sd["edge_detector.edge_conv.bias"])
         for i in range(3):
             p = f"decoder.decoder_blocks.{i}."
-            conv3(p + "conv1.weight", p + "conv1.bias", p + "bn1.", f"dec{i}a")
+            conv3(p + "conv1.weight", p + "conv1.bias", p + "bn1.", f"dec{i}a", up2=(i == 2))
             conv3(p + "conv2.weight", p + "conv2.bias", p + "bn2.", f"dec{i}b")
             W[f"head{i}.w"] = f32(sd[f"decoder.pred_heads.{i}.weight"]).reshape(-1)
             W[f"head{i}.b"] = f32(sd[f"decoder.pred_heads.{i}.bias"])
@@ -436,8 +483,12 @@ class SPEGNet(nn.Module):
         ops.conv3x3(ws.u2, W["dec1a.w"], ws.d2a.view(-1, 128), bias=W["dec1a.b"], act=ops.ACT_RELU)
         ops.conv3x3(ws.d2a, W["dec1b.w"], ws.d2.view(-1, 128), bias=W["dec1b.b"], act=ops.ACT_RELU,
                     head_w=W["head1.w"], head_b=self._head_b["head1.b"], head_out=preds[1])
-        ops.upsample_concat(ws.d2, None, ws.u3)
-        ops.conv3x3(ws.u3, W["dec2a.w"], ws.d3a.view(-1, 64), bias=W["dec2a.b"], act=ops.ACT_RELU)
+        # stage 3 (no edge branch): x2 upsample folded into conv1 -- border-column corrections, then one N=256 conv on
+        # the 4h x 4h grid with a pixel-shuffle store
+        ops.up2_border_gather(ws.d2, ws.bord)
+        ops.linear(ws.bord[0], W["dec2a.dwl"], ws.corr[0])
+        ops.linear(ws.bord[1], W["dec2a.dwr"], ws.corr[1])
+        ops.conv3x3_up2(ws.d2, W["dec2a.wp"], ws.corr, W["dec2a.bp"], ws.d3a)
         # stage-3 features never reach HBM: only the fused head output is stored
         ops.conv3x3(ws.d3a, W["dec2b.w"], None, bias=W["dec2b.b"], act=ops.ACT_RELU, head_w=W["head2.w"],
                     head_b=self._head_b["head2.b"], head_out=preds[2])

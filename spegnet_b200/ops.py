@@ -88,6 +88,31 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bi
     _lib.check(rc, "spg_conv3x3_h16", dn)
 
 
+def up2_border_gather(x: torch.Tensor, out: torch.Tensor) -> None:
+    """x [B,H,W,C] h16 -> out [2, B*H, 9*C] h16 (left operand of the border-column correction GEMM of conv3x3_up2)."""
+    B, H, W, Cc = x.shape
+    if tuple(out.shape) != (2, B * H, 9 * Cc):
+        raise ValueError(f"out must be [2, {B * H}, {9 * Cc}], got {tuple(out.shape)}")
+    lib, dn = _lib_for(x)
+    rc = lib.spg_up2_border_gather_h16(_ptr(x, H16, "x"), _ptr(out, H16, "out"), B, H, W, Cc, _stream())
+    _lib.check(rc, "spg_up2_border_gather_h16", dn)
+
+
+def conv3x3_up2(x: torch.Tensor, w_phase: torch.Tensor, corr: torch.Tensor, bias4: torch.Tensor, out: torch.Tensor) -> None:
+    """out [B,2H,2W,Cout] = relu(conv3x3(bilinear_x2(x)) + bias) without materialising the upsampled map.
+    x [B,H,W,Cin] h16, w_phase [3*4*Cout, 9*Cin] h16, corr [2, B*H, 4*Cout] fp32, bias4 [4*Cout] fp32."""
+    B, H, W, Cin = x.shape
+    Cout = w_phase.shape[0] // 12
+    if tuple(w_phase.shape) != (12 * Cout, 9 * Cin):
+        raise ValueError(f"w_phase must be [12*Cout, 9*Cin], got {tuple(w_phase.shape)}")
+    if tuple(out.shape) != (B, 2 * H, 2 * W, Cout) or tuple(corr.shape) != (2, B * H, 4 * Cout):
+        raise ValueError("out / corr shape does not match x and w_phase")
+    lib, dn = _lib_for(x)
+    rc = lib.spg_conv3x3_up2_h16(_ptr(x, H16, "x"), _ptr(w_phase, H16, "w_phase"), _ptr(corr, torch.float32, "corr"),
+                                 B, H, W, Cin, Cout, _ptr(bias4, torch.float32, "bias4"), _ptr(out, H16, "out"), _stream())
+    _lib.check(rc, "spg_conv3x3_up2_h16", dn)
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, eps: float) -> None:
     M, Cc = x.shape
     lib, dn = _lib_for(y)

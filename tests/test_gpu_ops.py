@@ -283,3 +283,32 @@ def test_mask_stats_match_reference_quantisation_and_mae(ops, double_sigmoid):
         assert (got_q != ref_q).mean() < 2e-3
         ref_mae = M.score_pair(got_q, gt[i].numpy())["mae"]  # same mask -> the statistics must give the exact MAE
         assert abs(mae[i] - ref_mae) < 1e-12
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 128, 64, 64), (1, 16, 256, 128, 64), (3, 5, 128, 64, 32),
+                                             (8, 64, 256, 128, 64)])
+def test_conv3x3_up2_matches_interpolate_then_conv(ops, B, H, W, Cin, Cout):
+    """Fused bilinear x2 + 3x3 conv (+ folded bias, ReLU) against F.interpolate -> F.conv2d in fp32
+    (models/object_detection.py:219,230-232); the last shape is large enough for the CTA-pair instance."""
+    from spegnet_b200.model import up2_phase_weights
+
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H)
+    x = _bf(torch.randn(B, H, W, Cin, device="cuda", generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Cin)
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    main, dwl, dwr = up2_phase_weights(w)
+    bord = torch.empty(2, B * H, 9 * Cin, device="cuda", dtype=H16)
+    corr = torch.empty(2, B * H, 4 * Cout, device="cuda", dtype=torch.float32)
+    out = torch.empty(B, 2 * H, 2 * W, Cout, device="cuda", dtype=H16)
+    ops.up2_border_gather(x, bord)
+    ops.linear(bord[0], _bf(dwl).contiguous(), corr[0])
+    ops.linear(bord[1], _bf(dwr).contiguous(), corr[1])
+    ops.conv3x3_up2(x, _bf(main).contiguous(), corr, bias.repeat(4).contiguous(), out)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False)
+    ref = F.relu(F.conv2d(up, w, bias, padding=1)).permute(0, 2, 3, 1)
+    _close(out, ref, 2e-2, 1e-2)
+    # the border rows / columns are where the folded weights differ: check them on their own
+    for sl in (out[:, :2], out[:, -2:], out[:, :, :2], out[:, :, -2:]):
+        assert torch.isfinite(sl.float()).all()
+    _close(out[:, :, :2], ref[:, :, :2], 2e-2, 1e-2)
+    _close(out[:, :, -2:], ref[:, :, -2:], 2e-2, 1e-2)

@@ -112,3 +112,39 @@ def test_trunk_geometry_agrees_with_oracle():
     for a, b in zip(trunk_blocks(), block_specs(HieraConfig())):
         assert (a.index, a.stage, a.dim_in, a.dim_out, a.heads, a.window, a.q_pool) == (
             b.index, b.stage, b.dim_in, b.dim_out, b.heads, b.window, bool(b.q_stride))
+
+
+def test_up2_phase_weights_reproduce_interpolate_then_conv():
+    """Host-side weight folding of the fused `bilinear x2 -> conv3x3` kernel (spg_conv3x3_up2_h16): a low-resolution
+    zero-padded conv with one weight set per row class, plus the border-column correction, equals
+    conv2d(interpolate(x, 2x, bilinear), w, padding=1) (models/object_detection.py:219,230) to fp64 rounding."""
+    import torch.nn.functional as F
+
+    from spegnet_b200.model import up2_operators, up2_phase_weights
+
+    R = up2_operators()
+    assert float((R[0] - R[1])[:, :, 2].abs().max()) == 0.0 and float((R[2] - R[1])[:, :, 0].abs().max()) == 0.0
+    g = torch.Generator().manual_seed(0)
+    B, H, W, Ci, Co = 2, 6, 7, 4, 3
+    x = torch.randn(B, Ci, H, W, dtype=torch.float64, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, dtype=torch.float64, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False), w, padding=1)
+    main, dwl, dwr = up2_phase_weights(w)
+    main = main.view(3, 4 * Co, 9 * Ci)
+    xp = F.pad(x, (1, 1, 1, 1))
+    cols = torch.stack([xp[:, :, dy:dy + H, dx:dx + W] for dy in range(3) for dx in range(3)], dim=1)
+    A = cols.permute(0, 3, 4, 1, 2).reshape(B, H, W, 9 * Ci)
+    out = torch.zeros(B, H, W, 4 * Co, dtype=torch.float64)
+    cls_of = lambda y: 0 if y == 0 else (2 if y == H - 1 else 1)  # noqa: E731
+    for y in range(H):
+        out[:, y] = A[:, y] @ main[cls_of(y)].t()
+    for col, dW in ((0, dwl), (W - 1, dwr)):
+        for y in range(H):
+            a = torch.zeros(B, 9 * Ci, dtype=torch.float64)
+            for dy in range(3):
+                if 0 <= y + dy - 1 < H:
+                    k = (cls_of(y) * 3 + dy) * Ci
+                    a[:, k:k + Ci] = x[:, :, y + dy - 1, col]
+            out[:, y, col] += a @ dW.t()
+    got = out.reshape(B, H, W, 2, 2, Co).permute(0, 5, 1, 3, 2, 4).reshape(B, Co, 2 * H, 2 * W)
+    assert float((got - ref).abs().max()) < 1e-12

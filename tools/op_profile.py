@@ -17,7 +17,7 @@ from spegnet_b200 import SPEGNet, ops  # noqa: E402
 
 CFG = {"encoder": {"config_path": "", "checkpoint_path": "", "variant": "large"}}
 NAMES = ["patchify", "linear", "layernorm", "maxpool2x2", "window_attention", "cast_h16", "fusion_combine", "pooled_mlp",
-         "scale_channels", "row_sums", "easpp_branches", "conv3x3", "upsample_concat", "mask_stats"]
+         "scale_channels", "row_sums", "easpp_branches", "conv3x3", "upsample_concat", "mask_stats", "conv3x3_up2", "up2_border_gather"]
 
 
 def sig(name, a, kw):
@@ -30,6 +30,9 @@ def sig(name, a, kw):
         x, w = a[0], a[1]
         return f"conv3x3 {tuple(x.shape)} -> {w.shape[0]} head={int(kw.get('head_w') is not None)}", \
             2.0 * x.shape[0] * x.shape[1] * x.shape[2] * w.shape[0] * w.shape[1]
+    if name == "conv3x3_up2":
+        x, w = a[0], a[1]
+        return f"conv3x3_up2 {tuple(x.shape)} -> 4x{w.shape[0] // 12}", 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * (w.shape[0] // 3) * w.shape[1]
     if name == "window_attention":
         return f"attention B,H,W,D,heads,win,pool={a[2:]}", 0.0
     if name == "layernorm":
