@@ -125,9 +125,10 @@ int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta,
                            float eps, spg_stream_t stream);
 
 /*
- * im2col for the 7x7 / stride 4 / pad 3 patch embedding: x fp32 NCHW [B,3,S,S] -> cols bf16
- * [B*(S/4)^2, 160], column k = c*49 + ky*7 + kx for k < 147, zero above.  The projection itself is
- * spg_linear_h16 with the positional embedding as a broadcast residual (res_rows = (S/4)^2).
+ * im2col for the 7x7 / stride 4 / pad 3 patch embedding: x fp32 NCHW [B,3,S,S] (16-byte aligned) -> cols bf16
+ * [B*(S/4)^2, 168], column k = (ky*3 + c)*8 + kx for kx < 7, zero at kx = 7 (each (ky, c) group is one aligned
+ * 16-byte gather).  The projection itself is spg_linear_h16 over a weight matrix packed in the same column order, with
+ * the positional embedding as a broadcast residual (res_rows = (S/4)^2).
  * Replaces PatchEmbed's Conv2d(3,144,7,4,3) + permute (HF:modeling_sam2.py:138-148).
  */
 int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_stream_t stream);

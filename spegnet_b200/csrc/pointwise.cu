@@ -85,31 +85,32 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// Patchify: NCHW fp32 image -> im2col rows for the 7x7 / stride 4 / pad 3 patch embedding,
-// k = c*49 + ky*7 + kx, zero-padded from 147 to 160 columns (bf16). One thread per (row, 8 columns).
+// Patchify: NCHW fp32 image -> im2col rows for the 7x7 / stride 4 / pad 3 patch embedding (bf16).
+// Column order k = (ky*3 + c)*8 + kx (kx = 0..6, slot 7 is zero): 168 columns.  The 7 taps of one (ky, c) sit at
+// ix = 4*ox - 3 .. 4*ox + 3, i.e. elements 1..7 of the 16-byte aligned pair x[4*ox - 4 .. 4*ox + 3]: one thread =
+// two float4 loads + one 16-byte store, with no per-element index arithmetic (550 -> 220 us at batch 64).  The weight
+// matrix is packed in the same column order on the host (model.py).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, uint16_t* __restrict__ cols, int B,
-                                                       int S) {
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, uint4* __restrict__ cols, int B, int S) {
     const int G = S >> 2;
-    const long long total = static_cast<long long>(B) * G * G * 20;
+    const long long total = static_cast<long long>(B) * G * G * 21;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
-        const int kv = idx % 20;
-        const long long row = idx / 20;
+        const int kc = idx % 21;  // ky*3 + c
+        const long long row = idx / 21;
         const int ox = row % G, oy = (row / G) % G, b = row / (static_cast<long long>(G) * G);
-        float f[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int k = kv * 8 + i;
-            float val = 0.f;
-            if (k < 147) {
-                const int c = k / 49, r = k - c * 49, ky = r / 7, kx = r - ky * 7;
-                const int iy = oy * 4 + ky - 3, ix = ox * 4 + kx - 3;
-                if (iy >= 0 && iy < S && ix >= 0 && ix < S)
-                    val = __ldg(x + ((static_cast<size_t>(b) * 3 + c) * S + iy) * S + ix);
+        const int ky = kc / 3, c = kc - ky * 3;
+        const int iy = oy * 4 + ky - 3;
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (iy >= 0 && iy < S) {
+            const float4* line = reinterpret_cast<const float4*>(x + ((static_cast<size_t>(b) * 3 + c) * S + iy) * S);
+            const float4 hi = __ldg(line + ox);  // ix = 4*ox .. 4*ox + 3
+            f[3] = hi.x; f[4] = hi.y; f[5] = hi.z; f[6] = hi.w;
+            if (ox > 0) {
+                const float4 lo = __ldg(line + ox - 1);  // ix = 4*ox - 4 .. 4*ox - 1 (the first is not a tap)
+                f[0] = lo.y; f[1] = lo.z; f[2] = lo.w;
             }
-            f[i] = val;
         }
-        reinterpret_cast<uint4*>(cols)[idx] = pack8(f);
+        cols[idx] = pack8(f);
     }
 }
 
@@ -161,39 +162,65 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, int out) {
 }
 
 // out[b,y,x,:] = concat(bilinear(src0)[C0], bilinear(src1)[C1]) in bf16 NHWC; src1 may be absent (C1 = 0).
-// One block per output row (b, oy): the vertical interpolation coefficients are block constants and the threads
-// sweep (ox, 8-channel vector) with coalesced 16-byte stores; neighbouring threads share source lines in L1.
+// One block per PAIR of output rows; a thread produces a 2x2 block of output pixels for one 8-channel vector from a
+// 3x3 patch of its source (for an integer scale >= 2 the four outputs read at most 3 source rows x 3 source columns):
+// 2.25 16-byte loads per 16-byte store instead of 4, and one set of interpolation coordinates per 4 outputs
+// (measured: 2.1 -> 2.9 TB/s of output).  Arithmetic order per output is ATen's: wy0 (wx0 a + wx1 b) + wy1 (wx0 c + wx1 d).
 __global__ void __launch_bounds__(256)
 upcat_kernel(const uint4* __restrict__ s0, int h0, int w0, int c0v, const uint4* __restrict__ s1, int h1, int w1,
              int c1v, uint4* __restrict__ out, int Ho, int Wo) {
     const int cv = c0v + c1v;
-    const int oy = blockIdx.x, b = blockIdx.y;
-    const Lerp ly0 = lerp_coord(oy, h0, Ho);
-    const Lerp ly1 = c1v > 0 ? lerp_coord(oy, h1, Ho) : ly0;
-    uint4* orow = out + (static_cast<size_t>(b) * Ho + oy) * Wo * cv;
-    const int total = Wo * cv;
+    const int by = blockIdx.x, b = blockIdx.y;
+    const int half_w = Wo >> 1;
+    const int total = half_w * cv;
+    uint4* orow0 = out + (static_cast<size_t>(b) * Ho + 2 * by) * Wo * cv;
+    uint4* orow1 = orow0 + static_cast<size_t>(Wo) * cv;
     for (int t = threadIdx.x; t < total; t += 256) {
-        const int ox = t / cv;
-        const int c = t - ox * cv;
+        const int bx = t / cv;
+        const int c = t - bx * cv;
         const uint4* src;
         int h, w, ncv, cc;
-        Lerp ly;
         if (c < c0v) {
-            src = s0; h = h0; w = w0; ncv = c0v; cc = c; ly = ly0;
+            src = s0; h = h0; w = w0; ncv = c0v; cc = c;
         } else {
-            src = s1; h = h1; w = w1; ncv = c1v; cc = c - c0v; ly = ly1;
+            src = s1; h = h1; w = w1; ncv = c1v; cc = c - c0v;
         }
-        const Lerp lx = lerp_coord(ox, w, Wo);
+        const Lerp ya = lerp_coord(2 * by, h, Ho), yb = lerp_coord(2 * by + 1, h, Ho);
+        const Lerp xa = lerp_coord(2 * bx, w, Wo), xb = lerp_coord(2 * bx + 1, w, Wo);
+        // patch rows {ya.i0, ya.i1, yb.i1} and columns {xa.i0, xa.i1, xb.i1}; yb.i0 / xb.i0 coincide with one of the first two
+        const int rows[3] = {ya.i0, ya.i1, yb.i1};
+        const int cols[3] = {xa.i0, xa.i1, xb.i1};
         const size_t img = static_cast<size_t>(b) * h * w;
-        float a[8], bq[8], cq[8], d[8], r[8];
-        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i0) * ncv + cc), a);
-        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i0) * w + lx.i1) * ncv + cc), bq);
-        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i0) * ncv + cc), cq);
-        unpack8(__ldg(src + (img + static_cast<size_t>(ly.i1) * w + lx.i1) * ncv + cc), d);
+        float p[3][3][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            r[i] = ly.w0 * (lx.w0 * a[i] + lx.w1 * bq[i]) + ly.w1 * (lx.w0 * cq[i] + lx.w1 * d[i]);
-        orow[t] = pack8(r);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                unpack8(__ldg(src + (img + static_cast<size_t>(rows[r]) * w + cols[q]) * ncv + cc), p[r][q]);
+        const bool yb0_first = yb.i0 == ya.i0, xb0_first = xb.i0 == xa.i0;
+        float o[2][2][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            // horizontal interpolation of the three patch rows at the two output columns
+            float hx[3][2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                hx[r][0] = xa.w0 * p[r][0][i] + xa.w1 * p[r][1][i];
+                const float left = xb0_first ? p[r][0][i] : p[r][1][i];
+                hx[r][1] = xb.w0 * left + xb.w1 * p[r][2][i];
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                o[0][q][i] = ya.w0 * hx[0][q] + ya.w1 * hx[1][q];
+                const float top = yb0_first ? hx[0][q] : hx[1][q];
+                o[1][q][i] = yb.w0 * top + yb.w1 * hx[2][q];
+            }
+        }
+        const size_t off = static_cast<size_t>(2 * bx) * cv + c;
+        orow0[off] = pack8(o[0][0]);
+        orow0[off + cv] = pack8(o[0][1]);
+        orow1[off] = pack8(o[1][0]);
+        orow1[off + cv] = pack8(o[1][1]);
     }
 }
 
@@ -508,8 +535,9 @@ extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const f
 extern "C" int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_stream_t stream) {
     SPG_CHECK_ARG(x && cols, "null pointer");
     SPG_CHECK_ARG(B > 0 && S > 0 && S % 4 == 0, "bad image size S=%d", S);
-    const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * 20;
-    patchify_kernel<<<capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint16_t*>(cols), B, S);
+    SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
+    const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * 21;
+    patchify_kernel<<<capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(cols), B, S);
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -538,7 +566,11 @@ extern "C" int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0,
     SPG_CHECK_ARG(src0 && out, "null pointer");
     SPG_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0 && c0 > 0 && c1 >= 0, "channel counts must be multiples of 8");
     SPG_CHECK_ARG(c1 == 0 || src1 != nullptr, "src1 is NULL but c1 > 0");
-    upcat_kernel<<<dim3(Ho, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    SPG_CHECK_ARG(Ho % 2 == 0 && Wo % 2 == 0, "output size must be even");
+    SPG_CHECK_ARG(Ho % h0 == 0 && Ho / h0 >= 2 && Wo % w0 == 0 && Wo / w0 >= 2, "src0 must be upsampled by an integer factor >= 2");
+    SPG_CHECK_ARG(c1 == 0 || (Ho % h1 == 0 && Ho / h1 >= 2 && Wo % w1 == 0 && Wo / w1 >= 2),
+                  "src1 must be upsampled by an integer factor >= 2");
+    upcat_kernel<<<dim3(Ho / 2, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(src0), h0, w0, c0 / 8, static_cast<const uint4*>(src1), h1, w1, c1 / 8,
         static_cast<uint4*>(out), Ho, Wo);
     SPG_LAUNCHED();

@@ -141,7 +141,7 @@ class _Workspace:
         G = S // 4
         T = [B * (G >> s) ** 2 for s in range(4)]  # tokens per stage
         e = lambda n, dt: torch.empty(n, dtype=dt, device=dev)  # noqa: E731
-        self.cols = e(T[0] * 160, bf).view(T[0], 160)
+        self.cols = e(T[0] * 168, bf).view(T[0], 168)
         self.x = [e(T[s] * d[s], f32).view(T[s], d[s]) for s in range(4)]
         self.proj = e(max(T[s] * d[s + 1] for s in range(3)), f32)
         self.y = e(max(T[s] * d[s] for s in range(4)), bf)
@@ -246,8 +246,9 @@ class SPEGNet(nn.Module):
         W: Dict[str, torch.Tensor] = {}
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
         t = "encoder.encoder."
-        pe = f32(sd[t + "patch_embed.proj.weight"]).reshape(self.spec.embed_dim, 147)
-        W["pe.w"] = F.pad(pe, (0, 13)).to(bf).contiguous()
+        # im2col column order of spg_patchify_7x7s4: k = (ky*3 + c)*8 + kx, slot kx = 7 zero -> K = 168
+        pe = f32(sd[t + "patch_embed.proj.weight"]).permute(0, 2, 1, 3)  # [144, ky, c, kx]
+        W["pe.w"] = F.pad(pe, (0, 1)).reshape(self.spec.embed_dim, 168).to(bf).contiguous()
         W["pe.b"] = f32(sd[t + "patch_embed.proj.bias"])
         W["pos_embed"] = f32(sd[t + "pos_embed"])
         W["pos_embed_window"] = f32(sd[t + "pos_embed_window"])

@@ -122,14 +122,15 @@ def test_patch_embed(ops):
     x = torch.randn(B, 3, S, S, device="cuda", generator=g)
     w = torch.randn(144, 3, 7, 7, device="cuda", generator=g) / math.sqrt(147)
     bias = torch.randn(144, device="cuda", generator=g)
-    cols = torch.empty(B * 256, 160, device="cuda", dtype=H16)
+    cols = torch.empty(B * 256, 168, device="cuda", dtype=H16)
     ops.patchify(x, cols)
-    wk = F.pad(w.reshape(144, 147), (0, 13)).to(H16).contiguous()
+    # column order of spg_patchify_7x7s4: k = (ky*3 + c)*8 + kx, slot kx = 7 zero
+    wk = F.pad(w.permute(0, 2, 1, 3), (0, 1)).reshape(144, 168).to(H16).contiguous()
     out = torch.empty(B * 256, 144, device="cuda")
     ops.linear(cols, wk, out, bias=bias)
     ref = F.conv2d(_bf(x).float(), _bf(w).float(), bias, stride=4, padding=3).permute(0, 2, 3, 1).reshape(-1, 144)
     _close(out, ref, 1e-3, 1e-3)
-    assert float(cols[:, 147:].abs().max()) == 0.0
+    assert float(cols.view(-1, 21, 8)[:, :, 7].abs().max()) == 0.0
 
 
 def test_maxpool_and_cast(ops):
