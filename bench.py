@@ -294,7 +294,7 @@ def main():
 
     # ---- instrumented GEMM/conv timing (dominant kernel) -------------------------------------------------
     gemm_events = []
-    real_linear, real_conv = ops.linear, ops.conv3x3
+    real_linear, real_conv, real_conv_up2 = ops.linear, ops.conv3x3, ops.conv3x3_up2
 
     def timed_linear(a, w, out, **kw):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -311,6 +311,14 @@ def main():
         e1.record()
         gemm_events.append((e0, e1, 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * w.shape[0] * w.shape[1]))
 
+    def timed_conv_up2(x, w_phase, corr, bias4, out):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        real_conv_up2(x, w_phase, corr, bias4, out)
+        e1.record()
+        # 4 phases x Cout outputs per low-resolution pixel over K = 9*Cin: the FLOPs of the 3x3 conv on the 2x grid
+        gemm_events.append((e0, e1, 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * (w_phase.shape[0] // 3) * w_phase.shape[1]))
+
     with torch.no_grad():
         for i in range(args.warmup):
             step(i)
@@ -321,7 +329,7 @@ def main():
         if rank == 0:
             sampler.start()
         _lib.reset_launch_count()
-        ops.linear, ops.conv3x3 = timed_linear, timed_conv
+        ops.linear, ops.conv3x3, ops.conv3x3_up2 = timed_linear, timed_conv, timed_conv_up2
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         t0.record()
@@ -329,7 +337,7 @@ def main():
             step(i)
         t1.record()
         torch.cuda.synchronize()
-        ops.linear, ops.conv3x3 = real_linear, real_conv
+        ops.linear, ops.conv3x3, ops.conv3x3_up2 = real_linear, real_conv, real_conv_up2
         if dist is not None:
             dist.barrier()
         launches = _lib.launch_count()
