@@ -206,7 +206,7 @@ int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, con
 
 /*
  * Mask quantisation of the reference's metric wrapper on the GPU (utils/metrics.py:205-210): mask = uint8(
- * sigmoid(logit) * 255) with truncation (double_sigmoid = 1: sigmoid applied twice, the evaluator path,
+ * sigmoid(logit) * 255) with truncation (any HW; double_sigmoid = 1: sigmoid applied twice, the evaluator path,
  * engine/evaluator.py:544 + utils/metrics.py:209), gt is uint8 with foreground > 128.  stats[b][8] (uint32) =
  * {255 - min q, max q, #gt foreground, sum q over gt background, sum q over gt foreground, 0, 0, 0}: integer
  * partials from which MAE after the min-max normalisation of py_sod_metrics follows exactly; they are what the
@@ -235,6 +235,26 @@ int spg_sod_gt_prepare_u8(const unsigned char* gt, int B, int H, int W, int* nea
 int spg_sod_scores_u8(const unsigned char* pred, const unsigned char* gt, const int* nearest,
                       const unsigned long long* gt_stats, int B, int H, int W, double* scores, void* workspace,
                       size_t ws_bytes, spg_stream_t stream);
+
+/*
+ * Image preprocessing of the reference on the GPU: CODImageProcessor.process_image (utils/image_processor.py:114-134):
+ * img uint8 HWC RGB [H,W,3] (device) -> /255 -> F.interpolate(size=(S,S), mode='bilinear', align_corners=False,
+ * antialias=True) -> (x - mean) / std -> out fp32 CHW [3,S,S] (the model's input layout).  The resampler restates ATen's
+ * separable anti-aliasing kernel (triangle filter of support max(in/out, 1); width, then height) with its index
+ * arithmetic, so windows and weights are ATen's.  mean3 / std3 are HOST arrays of 3 floats (ImageNet statistics in the
+ * reference); workspace = spg_preprocess_workspace_bytes(H, W, S) bytes of device scratch.
+ */
+size_t spg_preprocess_workspace_bytes(int H, int W, int S);
+int spg_preprocess_rgb_u8(const unsigned char* img, int H, int W, float* out, int S, const float* mean3,
+                          const float* std3, void* workspace, size_t ws_bytes, spg_stream_t stream);
+
+/*
+ * dst[b] = F.interpolate(src[b], size=(Ho,Wo), mode='bilinear', align_corners=False) for fp32 maps [B,Hi,Wi], followed
+ * by sigmoid when apply_sigmoid != 0: the per-image resize of the finest prediction / edge map to the original or
+ * ground-truth size (engine/predictor.py:350-365, engine/evaluator.py:539-554).
+ */
+int spg_resize_bilinear_f32(const float* src, int B, int Hi, int Wi, float* dst, int Ho, int Wo, int apply_sigmoid,
+                            spg_stream_t stream);
 
 /* bf16 NHWC [B,HW,C] -> fp32 NCHW [B,C,HW] (materialises `features` entries of the output dict on demand). */
 int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream);

@@ -54,6 +54,8 @@ SIGNATURES = {
     "spg_easpp_branches": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(C.c_int), _P],
     "spg_nhwc_h16_to_nchw_f32": [_P, _P, _I, _I, _I, _P],
     "spg_mask_stats_u8": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "spg_preprocess_rgb_u8": [_P, _I, _I, _P, _I, C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_size_t, _P],
+    "spg_resize_bilinear_f32": [_P, _I, _I, _I, _P, _I, _I, _I, _P],
     "spg_sod_gt_prepare_u8": [_P, _I, _I, _I, _P, _P, _P, C.c_size_t, _P],
     "spg_sod_scores_u8": [_P, _P, _P, _P, _I, _I, _I, _P, _P, C.c_size_t, _P],
     "spg_device_check": [],
@@ -65,6 +67,7 @@ _SPECIAL = {
     "spg_launch_count": ([], C.c_longlong),
     "spg_launch_count_reset": ([], None),
     "spg_sod_workspace_bytes": ([_I, _I, _I], C.c_size_t),
+    "spg_preprocess_workspace_bytes": ([_I, _I, _I], C.c_size_t),
 }
 EXPORTS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

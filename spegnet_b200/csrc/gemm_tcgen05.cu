@@ -563,7 +563,8 @@ int pick_block_n(int N) {
         const int padded = (N + 255) / 256 * 256;
         if ((padded - N) * 100 <= 12 * N) return 256;
     }
-    for (int bn = 256; bn >= 16; bn -= 16)
+    static const int max_bn_env = [] { const char* e = getenv("SPG_GEMM_MAX_BN"); return e ? atoi(e) : 256; }();  // tuning
+    for (int bn = max_bn_env; bn >= 16; bn -= 16)
         if (N % bn == 0) return bn;
     return 0;
 }

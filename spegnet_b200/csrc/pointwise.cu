@@ -490,6 +490,39 @@ mask_stats_kernel(const float4* __restrict__ logits, const uchar4* __restrict__ 
     }
 }
 
+// Same, one pixel per thread iteration: image sizes that are not a multiple of 4 (original-resolution ground truth).
+__global__ void __launch_bounds__(256)
+mask_stats_scalar_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ gt,
+                         unsigned char* __restrict__ mask, unsigned* __restrict__ stats, int HW, int double_sigmoid) {
+    const int b = blockIdx.y;
+    unsigned inv_min = 0, mx = 0, nfg = 0, sbg = 0, sfg = 0;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
+        float p = 1.f / (1.f + expf(-logits[static_cast<size_t>(b) * HW + i]));
+        if (double_sigmoid) p = 1.f / (1.f + expf(-p));
+        const unsigned q = static_cast<unsigned>(p * 255.f);
+        mask[static_cast<size_t>(b) * HW + i] = static_cast<unsigned char>(q);
+        inv_min = max(inv_min, 255u - q);
+        mx = max(mx, q);
+        if (gt[static_cast<size_t>(b) * HW + i] > 128) { ++nfg; sfg += q; } else { sbg += q; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        inv_min = max(inv_min, __shfl_xor_sync(0xffffffffu, inv_min, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        nfg += __shfl_xor_sync(0xffffffffu, nfg, o);
+        sbg += __shfl_xor_sync(0xffffffffu, sbg, o);
+        sfg += __shfl_xor_sync(0xffffffffu, sfg, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        unsigned* st = stats + b * 8;
+        atomicMax(st + 0, inv_min);
+        atomicMax(st + 1, mx);
+        atomicAdd(st + 2, nfg);
+        atomicAdd(st + 3, sbg);
+        atomicAdd(st + 4, sfg);
+    }
+}
+
 inline unsigned blocks_for(long long total, int per_block = 256) {
     return static_cast<unsigned>((total + per_block - 1) / per_block);
 }
@@ -632,9 +665,15 @@ extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* d
 extern "C" int spg_mask_stats_u8(const float* logits, const unsigned char* gt, unsigned char* mask, unsigned* stats,
                                  int B, int HW, int double_sigmoid, spg_stream_t stream) {
     SPG_CHECK_ARG(logits && gt && mask && stats, "null pointer");
-    SPG_CHECK_ARG(B > 0 && HW > 0 && HW % 4 == 0, "mask_stats needs HW %% 4 == 0");
+    SPG_CHECK_ARG(B > 0 && HW > 0, "bad shape B=%d HW=%d", B, HW);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SPG_CHECK_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * 8 * sizeof(unsigned), st));
+    if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(gt) & 3) ||
+        (reinterpret_cast<uintptr_t>(mask) & 3)) {
+        mask_stats_scalar_kernel<<<dim3(min(64, (HW + 255) / 256), B), 256, 0, st>>>(logits, gt, mask, stats, HW, double_sigmoid);
+        SPG_LAUNCHED();
+        return SPG_OK;
+    }
     const int per_img = min(64, (HW / 4 + 255) / 256);
     mask_stats_kernel<<<dim3(per_img, B), 256, 0, st>>>(reinterpret_cast<const float4*>(logits),
                                                         reinterpret_cast<const uchar4*>(gt),

@@ -9,8 +9,9 @@ means over images (:447-457).  Here: forward -> ``mask_stats`` (double sigmoid +
 exchange one ``[ceil(N/world), 6]`` fp64 all-gather per dataset (``sharded.gather_rows``), after which every rank
 averages in index order -- the result does not depend on the world size.
 
-Same-size ground truth only (the synthetic COD10K-sized set of BASELINE config 4); per-image resize to a different
-ground-truth size is not built yet and raises.
+Ground truth may be a [b,S,S] tensor at the prediction's size (the synthetic COD10K-sized set of BASELINE config 4:
+one batched scoring call) or a list of [h_i, w_i] masks at their original sizes, in which case every prediction is
+resized to its own mask first (`spg_resize_bilinear_f32` + sigmoid), as engine/evaluator.py:539-544 does.
 """
 from __future__ import annotations
 
@@ -18,7 +19,7 @@ from typing import Callable, Dict, List, Tuple
 
 import torch
 
-from . import metrics, sharded
+from . import metrics, ops, sharded
 
 # (indices) -> (images fp32 [b,3,S,S] on the model's device, ground truth uint8 [b,S,S] with foreground > 128)
 BatchFn = Callable[[List[int]], Tuple[torch.Tensor, torch.Tensor]]
@@ -58,10 +59,18 @@ def score_batch(model, images: torch.Tensor, gt_u8: torch.Tensor) -> torch.Tenso
         return torch.zeros(0, 5, dtype=torch.float64, device=images.device)
     out = model(images)
     logits = out["predictions"][-1]
-    if tuple(logits.shape[-2:]) != tuple(gt_u8.shape[-2:]):
-        raise NotImplementedError("ground truth of a different size than the prediction: per-image resize is not built")
-    rows, _ = metrics.per_sample(logits, metrics.PreparedGT(gt_u8), double_sigmoid=True)
-    return rows
+    if isinstance(gt_u8, torch.Tensor) and tuple(logits.shape[-2:]) == tuple(gt_u8.shape[-2:]):
+        rows, _ = metrics.per_sample(logits, metrics.PreparedGT(gt_u8), double_sigmoid=True)
+        return rows
+    # original-size masks: resize + sigmoid per image (engine/evaluator.py:539-544), then the wrapper's own
+    # sigmoid * 255 -> byte (utils/metrics.py:209-210) and the five scores
+    rows = []
+    for i in range(logits.shape[0]):
+        g = gt_u8[i]
+        prob = ops.resize_bilinear(logits[i, 0].contiguous()[None], tuple(g.shape[-2:]), sigmoid=True)
+        rows.append(metrics.per_sample(prob, metrics.PreparedGT(metrics.quantise_gt(g.reshape(1, *g.shape[-2:]))),
+                                       double_sigmoid=False)[0])
+    return torch.cat(rows)
 
 
 @torch.no_grad()

@@ -269,3 +269,45 @@ def sod_scores(pred_u8: torch.Tensor, gt_u8: torch.Tensor, nearest: torch.Tensor
                                _stream())
     _lib.check(rc, "spg_sod_scores_u8", dn)
     return scores
+
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)  # utils/image_processor.py:67-68
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def preprocess_rgb(img_u8: torch.Tensor, size: int, mean=IMAGENET_MEAN, std=IMAGENET_STD,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 HWC RGB image on the device -> fp32 [3,size,size], the reference's process_image
+    (utils/image_processor.py:114-134: /255, antialiased bilinear resize, ImageNet normalisation).  See
+    spg_preprocess_rgb_u8."""
+    if img_u8.dim() != 3 or img_u8.shape[2] != 3:
+        raise ValueError(f"expected a uint8 [H,W,3] image, got {tuple(img_u8.shape)}")
+    H, W, _ = img_u8.shape
+    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    if out is None:
+        out = torch.empty(3, size, size, dtype=torch.float32, device=img_u8.device)
+    nbytes = int(lib.spg_preprocess_workspace_bytes(H, W, size))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=img_u8.device)
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    rc = lib.spg_preprocess_rgb_u8(_ptr(img_u8, torch.uint8, "img"), H, W, _ptr(out, torch.float32, "out"), size, m, s,
+                                   _ptr(ws, torch.uint8, "workspace"), nbytes, _stream())
+    _lib.check(rc, "spg_preprocess_rgb_u8", dn)
+    return out
+
+
+def resize_bilinear(src: torch.Tensor, size, sigmoid: bool = False) -> torch.Tensor:
+    """fp32 [B,1,H,W] / [B,H,W] -> the same rank at `size`, F.interpolate(mode='bilinear', align_corners=False)
+    [+ sigmoid]: engine/predictor.py:350-365, engine/evaluator.py:539-554.  See spg_resize_bilinear_f32."""
+    ho, wo = int(size[0]), int(size[1])
+    lead = src.shape[:-2]
+    hi, wi = src.shape[-2:]
+    B = 1
+    for d in lead:
+        B *= int(d)
+    dst = torch.empty(*lead, ho, wo, dtype=torch.float32, device=src.device)
+    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    rc = lib.spg_resize_bilinear_f32(_ptr(src, torch.float32, "src"), B, hi, wi, _ptr(dst, torch.float32, "dst"), ho, wo,
+                                     int(sigmoid), _stream())
+    _lib.check(rc, "spg_resize_bilinear_f32", dn)
+    return dst

@@ -1,0 +1,86 @@
+"""Input / output side on the GPU (csrc/imageio.cu) through the C-ABI: preprocessing against the reference
+CODImageProcessor's own outputs (tests/golden/preprocess.npz) and against the oracle on fresh sizes; prediction resize
+against F.interpolate; the evaluator's original-size scoring path against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "preprocess.npz")
+# fp32 in both implementations; they differ in summation order of the <= 2*scale+1 filter taps and in the fused
+# (x - mean) / std rounding: a few ulp of an O(1) value
+TOL = 2e-6
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from spegnet_b200 import _lib, ops as _ops
+
+    assert _lib.load().spg_device_check() == 0
+    return _ops
+
+
+@pytest.mark.parametrize("name", ["down", "down_big", "up", "mixed", "same_w"])
+def test_preprocess_matches_reference_golden(ops, name):
+    g = np.load(GOLD)
+    got = ops.preprocess_rgb(torch.from_numpy(g[name + "_rgb"]).cuda(), int(g[name + "_target"])).cpu().numpy()
+    want = g[name + "_out"]
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= TOL * 4.5, np.abs(got - want).max()  # 1 / std amplifies by up to 4.46
+
+
+@pytest.mark.parametrize("h,w,target", [(683, 1024, 512), (512, 512, 512), (1500, 2000, 512), (300, 400, 512),
+                                        (768, 1024, 1024)])
+def test_preprocess_matches_oracle_at_real_sizes(ops, h, w, target):
+    from oracle.preprocess import process_image_array
+
+    rng = np.random.default_rng(h * 7 + w)
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    got = ops.preprocess_rgb(torch.from_numpy(rgb).cuda(), target).cpu()
+    want = process_image_array(rgb, target)
+    assert float((got - want).abs().max()) <= TOL * 4.5
+
+
+@pytest.mark.parametrize("hi,ho,wo,sig", [(512, 683, 1024, True), (512, 512, 512, False), (64, 301, 203, True),
+                                          (512, 300, 400, True), (128, 97, 131, False)])
+def test_resize_bilinear_matches_interpolate(ops, hi, ho, wo, sig):
+    g = torch.Generator(device="cuda").manual_seed(hi + ho)
+    x = torch.randn(3, 1, hi, hi, device="cuda", generator=g) * 4
+    got = ops.resize_bilinear(x, (ho, wo), sigmoid=sig)
+    want = F.interpolate(x, size=(ho, wo), mode="bilinear", align_corners=False)
+    want = want.sigmoid() if sig else want
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 5e-6
+
+
+def test_original_size_scoring_matches_oracle(ops, spread_sd):
+    """engine/evaluator.py:539-560 with masks at their original sizes: resize -> sigmoid -> MetricsProcessor."""
+    from oracle.preprocess import resize_logits
+    from oracle.sod_metrics import quantise_like_reference, score_pair
+    from spegnet_b200 import SPEGNet, evaluate
+
+    dev = torch.device("cuda", 0)
+    model = SPEGNet({"encoder": {"config_path": "", "checkpoint_path": "", "variant": "large"}})
+    model.load_state_dict(spread_sd)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(4)
+    images = torch.randn(2, 3, 256, 256, generator=g).to(dev)
+    sizes = [(301, 203), (180, 333)]
+    gts = []
+    for h, w in sizes:
+        yy, xx = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+        gts.append(((((yy - h / 2) / (h / 4)) ** 2 + ((xx - w / 2.5) / (w / 5)) ** 2) < 1).to(torch.uint8).mul(255).to(dev))
+    rows = evaluate.score_batch(model, images, gts).cpu()
+    with torch.no_grad():
+        logits = model(images)["predictions"][-1].cpu()
+    for i, (h, w) in enumerate(sizes):
+        prob = resize_logits(logits[i:i + 1], (h, w), sigmoid=True)[0, 0].numpy()
+        want = score_pair(quantise_like_reference(prob), gts[i].cpu().numpy())
+        for k, key in enumerate(("sm", "wfm", "mae", "em", "fm")):
+            assert abs(float(rows[i, k]) - want[key]) <= 2e-4, (i, key, float(rows[i, k]), want[key])
