@@ -84,3 +84,31 @@ def test_original_size_scoring_matches_oracle(ops, spread_sd):
         want = score_pair(quantise_like_reference(prob), gts[i].cpu().numpy())
         for k, key in enumerate(("sm", "wfm", "mae", "em", "fm")):
             assert abs(float(rows[i, k]) - want[key]) <= 2e-4, (i, key, float(rows[i, k]), want[key])
+
+
+def test_predict_single_matches_oracle_pipeline(ops, spread_sd):
+    """Predictor.predict_single end to end (engine/predictor.py:311-368): preprocess -> forward -> resize -> sigmoid on
+    the GPU against the fp32 CPU oracle of every stage; masks within the north star's 1e-2."""
+    from oracle.preprocess import process_image_array, resize_logits
+    from oracle.spegnet import spegnet_forward
+    from spegnet_b200 import SPEGNet, predict
+
+    dev = torch.device("cuda", 0)
+    model = SPEGNet({"encoder": {"config_path": "", "checkpoint_path": "", "variant": "large"}})
+    model.load_state_dict(spread_sd)
+    model = model.to(dev).eval()
+    rng = np.random.default_rng(3)
+    h, w = 300, 420
+    yy, xx = np.mgrid[:h, :w]
+    rgb = np.clip(127 + 90 * np.sin(xx / 17.0)[..., None] * np.array([1, .5, -1]) + 60 * np.cos(yy / 23.0)[..., None]
+                  + rng.normal(0, 20, (h, w, 3)), 0, 255).astype(np.uint8)
+    seg, edge = predict.predict_single(model, torch.from_numpy(rgb).to(dev), target_size=256, output_size=(h, w))
+    x = process_image_array(rgb, 256)[None]
+    ref = spegnet_forward(spread_sd, x)
+    want_seg = resize_logits(ref["predictions"][-1], (h, w))[0, 0]
+    want_edge = resize_logits(ref["edge"], (h, w))[0, 0]
+    assert tuple(seg.shape) == (h, w) and tuple(edge.shape) == (h, w)
+    assert float((seg.cpu() - want_seg).abs().max()) <= 1e-2
+    assert float((edge.cpu() - want_edge).abs().max()) <= 1e-2
+    mask = predict.binary_mask_u8(seg)
+    assert mask.dtype == torch.uint8 and int((mask.cpu().int() - (want_seg * 255).to(torch.uint8).int()).abs().max()) <= 3
