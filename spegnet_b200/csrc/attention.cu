@@ -88,7 +88,9 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
         for (int u = 0; u < 4; ++u) mbar_init(bar_u + 8u * u, 1);
         fence_barrier_init();
     }
+    pdl_launch_dependents();
     __syncthreads();
+    pdl_wait();  // everything above touched only shared memory / the tensor map; qkv is read below
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -283,6 +285,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
 // Tiny-window fallback on CUDA cores (block 8 of Hiera-L: 4 pooled queries x 16 keys per window):
 // one warp per (window, head, query), lanes over keys for the scores and over dims for the output.
 __global__ void __launch_bounds__(128) tiny_attention_kernel(const AttnParams p) {
+    pdl_prologue();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int total = p.B * p.nwx * p.nwy * p.heads * p.Nq;
@@ -387,7 +390,7 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     const bool mma_ok = big || quad;
     if (!mma_ok) {
         const long long warps = static_cast<long long>(nwin) * heads * p.Nq;
-        tiny_attention_kernel<<<static_cast<unsigned>((warps * 32 + 127) / 128), 128, 0, st>>>(p);
+        SPG_CHECK_CUDA((launch_pdl(tiny_attention_kernel, static_cast<unsigned>((warps * 32 + 127) / 128), 128, 0, st, p)));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         SPG_CHECK_LAUNCH();
         return SPG_OK;
@@ -407,9 +410,9 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     }
     dim3 grid(p.wpc > 1 ? nwin / p.wpc : nwin * p.qtiles, heads);
     if (p.Nk == 16)
-        window_attention_kernel<16><<<grid, kThreads, smem, st>>>(tmap, p);
+        SPG_CHECK_CUDA((launch_pdl(window_attention_kernel<16>, grid, kThreads, smem, st, tmap, p)));
     else
-        window_attention_kernel<64><<<grid, kThreads, smem, st>>>(tmap, p);
+        SPG_CHECK_CUDA((launch_pdl(window_attention_kernel<64>, grid, kThreads, smem, st, tmap, p)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;

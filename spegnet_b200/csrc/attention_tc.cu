@@ -86,9 +86,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();  // barriers / TMEM are set up; qkv (the previous kernel's output) is first read below
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -328,7 +330,7 @@ extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, in
         attr_set = true;
     }
     const int grid = p.items < sm_count() ? p.items : sm_count();
-    attention_tc_kernel<<<grid, kThreadsTc, kSmemTc, static_cast<cudaStream_t>(stream)>>>(tmain, ttail, p);
+    SPG_CHECK_CUDA((launch_pdl(attention_tc_kernel, grid, kThreadsTc, kSmemTc, static_cast<cudaStream_t>(stream), tmain, ttail, p)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;

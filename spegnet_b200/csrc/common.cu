@@ -3,6 +3,7 @@
 #include "half16.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -34,6 +35,11 @@ int sm_count() {
             cached = 148;
     }
     return cached;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SPG_PDL"); return e == nullptr || atoi(e) != 0; }();
+    return on;
 }
 
 namespace {

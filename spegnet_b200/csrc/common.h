@@ -65,4 +65,41 @@ int make_tmap_qkv_5d(CUtensorMap* out, const void* base, uint64_t BH, uint64_t W
 
 int sm_count();
 
+// ---------------------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+//     griddepcontrol.launch_dependents   -- the NEXT kernel in the stream may be scheduled as soon as every CTA of this
+//                                           one has started (its CTAs fill SMs as ours drain)
+//     griddepcontrol.wait                -- block until the PREVIOUS kernel has completed and its writes are visible
+// placed after the part of the prologue that touches no global data (barrier init, TMEM allocation, tensor-map
+// prefetch).  All global reads AND writes of a kernel come after its wait, so the stream's dependency semantics are
+// unchanged (no RAW / WAR hazard); what is hidden is the launch latency, the prologue and the tail of the previous
+// kernel -- 371 serialised launches per forward.  SPG_PDL=0 turns the attribute off (the instructions are then no-ops).
+// ---------------------------------------------------------------------------------------------------------------
+bool pdl_enabled();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 }  // namespace spg

@@ -181,10 +181,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             tmem_relinquish();
         }
     }
+    pdl_launch_dependents();
     tc_fence_before();
     if (kPair) cluster_sync_all();  // the peer's barriers / TMEM must exist before any remote arrive or 2-CTA MMA
     else __syncthreads();
     tc_fence_after();
+    pdl_wait();  // prologue done (barriers, TMEM, descriptor prefetch); operands of the previous kernel are read below
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -615,13 +617,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     cfg.blockDim = dim3(64 + 32 * a.epi_warps);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pair ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see common.h "Programmatic dependent launch"
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     // the combinations SPEGNet launches get a compile-time specialised epilogue; anything else runs the generic one
 #define SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, PAIR, EW)                                                         \
     do {                                                                                                           \

@@ -53,6 +53,7 @@ __device__ __forceinline__ float aa_weight(const AaWindow& w, int j) {
 // Horizontal pass: uint8 HWC -> fp32 [3][H][So] (values / 255 resampled along x).  Thread = (y, xo), 3 channels.
 __global__ void __launch_bounds__(256) aa_rows_kernel(const uint8_t* __restrict__ img, int H, int W, float* __restrict__ tmp,
                                                       int So, float scale) {
+    pdl_prologue();
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= static_cast<long long>(H) * So) return;
     const int xo = idx % So, y = idx / So;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(256) aa_rows_kernel(const uint8_t* __restrict_
 __global__ void __launch_bounds__(256) aa_cols_kernel(const float* __restrict__ tmp, int H, int So, float* __restrict__ out,
                                                       float scale, float m0, float m1, float m2, float s0, float s1,
                                                       float s2) {
+    pdl_prologue();
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= 3ll * So * So) return;
     const int xo = idx % So;
@@ -112,6 +114,7 @@ __global__ void __launch_bounds__(256) aa_cols_kernel(const float* __restrict__ 
 // Bilinear resize of fp32 maps, align_corners=False, ATen's coordinates: src = max(0, (dst + 0.5) * in/out - 0.5).
 __global__ void __launch_bounds__(256) resize_bilinear_kernel(const float* __restrict__ src, int hi, int wi,
                                                               float* __restrict__ dst, int ho, int wo, int apply_sigmoid) {
+    pdl_prologue();
     const int b = blockIdx.y;
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= static_cast<long long>(ho) * wo) return;
@@ -149,11 +152,11 @@ extern "C" int spg_preprocess_rgb_u8(const unsigned char* img, int H, int W, flo
     float* tmp = static_cast<float*>(workspace);
     const float sx = static_cast<float>(W) / static_cast<float>(S), sy = static_cast<float>(H) / static_cast<float>(S);
     const long long n1 = static_cast<long long>(H) * S;
-    aa_rows_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, st>>>(img, H, W, tmp, S, sx);
+    SPG_CHECK_CUDA((launch_pdl(aa_rows_kernel, static_cast<unsigned>((n1 + 255) / 256), 256, 0, st, img, H, W, tmp, S, sx)));
     SPG_LAUNCHED();
     const long long n2 = 3ll * S * S;
-    aa_cols_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(tmp, H, S, out, sy, mean3[0], mean3[1], mean3[2],
-                                                                           std3[0], std3[1], std3[2]);
+    SPG_CHECK_CUDA((launch_pdl(aa_cols_kernel, static_cast<unsigned>((n2 + 255) / 256), 256, 0, st, tmp, H, S, out, sy, mean3[0], mean3[1], mean3[2],
+                                                                           std3[0], std3[1], std3[2])));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -163,8 +166,7 @@ extern "C" int spg_resize_bilinear_f32(const float* src, int B, int Hi, int Wi, 
     SPG_CHECK_ARG(src && dst, "null pointer");
     SPG_CHECK_ARG(B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bad shape");
     const long long n = static_cast<long long>(Ho) * Wo;
-    resize_bilinear_kernel<<<dim3(static_cast<unsigned>((n + 255) / 256), B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, Hi, Wi, dst, Ho, Wo, apply_sigmoid);
+    SPG_CHECK_CUDA((launch_pdl(resize_bilinear_kernel, dim3(static_cast<unsigned>((n + 255) / 256), B), 256, 0, static_cast<cudaStream_t>(stream), src, Hi, Wi, dst, Ho, Wo, apply_sigmoid)));
     SPG_LAUNCHED();
     return SPG_OK;
 }

@@ -42,6 +42,7 @@ __constant__ double c_gauss7[49];
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gt_stats_kernel(const uint8_t* __restrict__ gt, int H, int W,
                                                        unsigned long long* __restrict__ stats) {
+    pdl_prologue();
     const int b = blockIdx.y;
     const int HW = H * W;
     unsigned long long n = 0, sy = 0, sx = 0;
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) gt_stats_kernel(const uint8_t* __restrict
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) ft_columns_kernel(const uint8_t* __restrict__ gt, int H, int W,
                                                          short* __restrict__ colfeat) {
+    pdl_prologue();
     const int x = blockIdx.x * 128 + threadIdx.x;
     const int b = blockIdx.y;
     if (x >= W) return;
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(128) ft_columns_kernel(const uint8_t* __restri
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) ft_rows_kernel(const short* __restrict__ colfeat, int H, int W,
                                                      short* __restrict__ stack, int* __restrict__ nearest) {
+    pdl_prologue();
     const int y = blockIdx.x * 64 + threadIdx.x;
     const int b = blockIdx.y;
     if (y >= H) return;
@@ -165,6 +168,7 @@ __device__ __forceinline__ void centroid(const unsigned long long* st, int H, in
 __global__ void __launch_bounds__(256) sod_hist_kernel(const uint8_t* __restrict__ pred, const uint8_t* __restrict__ gt,
                                                        const unsigned long long* __restrict__ gt_stats, int H, int W,
                                                        unsigned* __restrict__ hist) {
+    pdl_prologue();
     __shared__ unsigned sh[8 * 256];
     const int b = blockIdx.y;
     for (int i = threadIdx.x; i < 8 * 256; i += 256) sh[i] = 0;
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(256) sod_wfm_kernel(const uint8_t* __restrict_
                                                       const int* __restrict__ nearest, const unsigned* __restrict__ hist,
                                                       const unsigned long long* __restrict__ gt_stats, int H, int W,
                                                       double* __restrict__ partials) {
+    pdl_prologue();
     __shared__ double s_val[256];
     __shared__ double s_et[kTileH][kTileH + 1];
     __shared__ double s_red[2][8];
@@ -360,6 +365,7 @@ __global__ void __launch_bounds__(256) sod_finalize_kernel(const unsigned* __res
                                                            const unsigned long long* __restrict__ gt_stats,
                                                            const double* __restrict__ partials, int tiles, int H, int W,
                                                            double* __restrict__ scores) {
+    pdl_prologue();
     __shared__ double s_buf[8];
     __shared__ double s_fgh[256], s_bgh[256];
     __shared__ double s_f[256];
@@ -547,11 +553,11 @@ extern "C" int spg_sod_gt_prepare_u8(const unsigned char* gt, int B, int H, int 
     short* stack = colfeat + hw;
     SPG_CHECK_CUDA(cudaMemsetAsync(gt_stats, 0, static_cast<size_t>(B) * 4 * sizeof(unsigned long long), st));
     const int per_img = min(32, (H * W + 256 * 16 - 1) / (256 * 16));
-    gt_stats_kernel<<<dim3(per_img, B), 256, 0, st>>>(gt, H, W, gt_stats);
+    SPG_CHECK_CUDA((launch_pdl(gt_stats_kernel, dim3(per_img, B), 256, 0, st, gt, H, W, gt_stats)));
     SPG_LAUNCHED();
-    ft_columns_kernel<<<dim3((W + 127) / 128, B), 128, 0, st>>>(gt, H, W, colfeat);
+    SPG_CHECK_CUDA((launch_pdl(ft_columns_kernel, dim3((W + 127) / 128, B), 128, 0, st, gt, H, W, colfeat)));
     SPG_LAUNCHED();
-    ft_rows_kernel<<<dim3((H + 63) / 64, B), 64, 0, st>>>(colfeat, H, W, stack, nearest);
+    SPG_CHECK_CUDA((launch_pdl(ft_rows_kernel, dim3((H + 63) / 64, B), 64, 0, st, colfeat, H, W, stack, nearest)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -572,11 +578,11 @@ extern "C" int spg_sod_scores_u8(const unsigned char* pred, const unsigned char*
     const int tx = (W + kTile - 1) / kTile, ty = (H + kTile - 1) / kTile;
     SPG_CHECK_CUDA(cudaMemsetAsync(hist, 0, hist_bytes, st));
     const int per_img = min(32, (H * W + 256 * 16 - 1) / (256 * 16));
-    sod_hist_kernel<<<dim3(per_img, B), 256, 0, st>>>(pred, gt, gt_stats, H, W, hist);
+    SPG_CHECK_CUDA((launch_pdl(sod_hist_kernel, dim3(per_img, B), 256, 0, st, pred, gt, gt_stats, H, W, hist)));
     SPG_LAUNCHED();
-    sod_wfm_kernel<<<dim3(tx, ty, B), 256, 0, st>>>(pred, gt, nearest, hist, gt_stats, H, W, partials);
+    SPG_CHECK_CUDA((launch_pdl(sod_wfm_kernel, dim3(tx, ty, B), 256, 0, st, pred, gt, nearest, hist, gt_stats, H, W, partials)));
     SPG_LAUNCHED();
-    sod_finalize_kernel<<<B, 256, 0, st>>>(hist, gt_stats, partials, tx * ty, H, W, scores);
+    SPG_CHECK_CUDA((launch_pdl(sod_finalize_kernel, B, 256, 0, st, hist, gt_stats, partials, tx * ty, H, W, scores)));
     SPG_LAUNCHED();
     return SPG_OK;
 }

@@ -35,6 +35,7 @@ template <int LPR, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, uint16_t* __restrict__ y,
                                                         int M, int C, float eps, int rows_per_warp) {
+    pdl_prologue();
     constexpr int RPW = 32 / LPR;  // rows processed concurrently by one warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane % LPR, grp = lane / LPR;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // matrix is packed in the same column order on the host (model.py).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, uint4* __restrict__ cols, int B, int S) {
+    pdl_prologue();
     const int G = S >> 2;
     const long long total = static_cast<long long>(B) * G * G * 21;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool_kernel(const float4* __restrict__ x, float4* __restrict__ y, int B, int H,
                                                       int W, int C4) {
+    pdl_prologue();
     const int Ho = H >> 1, Wo = W >> 1;
     const long long total = static_cast<long long>(B) * Ho * Wo * C4;
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < total; idx += gridDim.x * 256ll) {
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float4* __restrict__
 
 // fp32 -> bf16 cast, 8 elements per thread.
 __global__ void __launch_bounds__(256) cast_kernel(const float4* __restrict__ x, uint4* __restrict__ y, long long n8) {
+    pdl_prologue();
     for (long long idx = blockIdx.x * 256ll + threadIdx.x; idx < n8; idx += gridDim.x * 256ll) {
         const float4 a = x[2 * idx], b = x[2 * idx + 1];
         y[idx] = make_uint4(pack2(a.x, a.y), pack2(a.z, a.w), pack2(b.x, b.y), pack2(b.z, b.w));
@@ -169,6 +173,7 @@ __device__ __forceinline__ Lerp lerp_coord(int dst, int in, int out) {
 __global__ void __launch_bounds__(256)
 upcat_kernel(const uint4* __restrict__ s0, int h0, int w0, int c0v, const uint4* __restrict__ s1, int h1, int w1,
              int c1v, uint4* __restrict__ out, int Ho, int Wo) {
+    pdl_prologue();
     const int cv = c0v + c1v;
     const int by = blockIdx.x, b = blockIdx.y;
     const int half_w = Wo >> 1;
@@ -234,6 +239,7 @@ __global__ void __launch_bounds__(128)
 fusion_combine_kernel(const float4* __restrict__ g2, const float4* __restrict__ g3, const float4* __restrict__ g4,
                       const float4* __restrict__ bias, uint2* __restrict__ fused, float4* __restrict__ partial, int Hs,
                       int C4) {
+    pdl_prologue();
     const int b = blockIdx.y, y = blockIdx.x;
     const int H3 = Hs >> 1, H4 = Hs >> 2;
     const Lerp ly3 = lerp_coord(y, H3, Hs), ly4 = lerp_coord(y, H4, Hs);
@@ -270,6 +276,7 @@ fusion_combine_kernel(const float4* __restrict__ g2, const float4* __restrict__ 
 // Per-row channel sums of a bf16 NHWC map (global-average-pool partials): one CTA per (image, row).
 __global__ void __launch_bounds__(128)
 row_sums_kernel(const uint2* __restrict__ x, float4* __restrict__ partial, int H, int W, int C4) {
+    pdl_prologue();
     const int b = blockIdx.y, y = blockIdx.x;
     for (int c = threadIdx.x; c < C4; c += blockDim.x) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -288,6 +295,7 @@ row_sums_kernel(const uint2* __restrict__ x, float4* __restrict__ partial, int H
 __global__ void __launch_bounds__(512)
 pooled_mlp_kernel(const float* __restrict__ partial, int rows, float inv_count, const float* __restrict__ W1,
                   const float* __restrict__ b1, int R, const float* __restrict__ W2, float* __restrict__ out, int C) {
+    pdl_prologue();
     extern __shared__ float sm[];
     float* mean = sm;          // [C]
     float* hidden = sm + C;    // [R]
@@ -322,6 +330,7 @@ pooled_mlp_kernel(const float* __restrict__ partial, int rows, float inv_count, 
 // x[b, p, c] *= gate[b, c]  (bf16 NHWC in place, 8 channels per thread)
 __global__ void __launch_bounds__(256)
 scale_channels_kernel(uint4* __restrict__ x, const float* __restrict__ gate, long long total, int HW, int C8) {
+    pdl_prologue();
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= total) return;
     const int c = idx % C8;
@@ -355,6 +364,7 @@ struct AsppParams {
 };
 
 __global__ void __launch_bounds__(256) aspp_kernel(const AsppParams p) {
+    pdl_prologue();
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
     const long long total = static_cast<long long>(p.B) * p.H * p.W * 16;
     if (idx >= total) return;
@@ -414,6 +424,7 @@ __global__ void __launch_bounds__(256) aspp_kernel(const AsppParams p) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 up2_border_gather_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int B, int H, int W, int C8) {
+    pdl_prologue();
     const long long total = 2ll * B * H * 9 * C8;
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= total) return;
@@ -434,6 +445,7 @@ up2_border_gather_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, i
 // bf16 NHWC -> fp32 NCHW (for the lazily materialised `features` entries of the output dict).
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, int HW, int C, long long total) {
+    pdl_prologue();
     const long long idx = blockIdx.x * 256ll + threadIdx.x;
     if (idx >= total) return;
     const int p = idx % HW;
@@ -452,6 +464,7 @@ nhwc_to_nchw_kernel(const uint16_t* __restrict__ x, float* __restrict__ y, int H
 __global__ void __launch_bounds__(256)
 mask_stats_kernel(const float4* __restrict__ logits, const uchar4* __restrict__ gt, uchar4* __restrict__ mask,
                   unsigned* __restrict__ stats, int HW4, int double_sigmoid) {
+    pdl_prologue();
     const int b = blockIdx.y;
     unsigned inv_min = 0, mx = 0, nfg = 0, sbg = 0, sfg = 0;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < HW4; i += gridDim.x * 256) {
@@ -494,6 +507,7 @@ mask_stats_kernel(const float4* __restrict__ logits, const uchar4* __restrict__ 
 __global__ void __launch_bounds__(256)
 mask_stats_scalar_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ gt,
                          unsigned char* __restrict__ mask, unsigned* __restrict__ stats, int HW, int double_sigmoid) {
+    pdl_prologue();
     const int b = blockIdx.y;
     unsigned inv_min = 0, mx = 0, nfg = 0, sbg = 0, sfg = 0;
     for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
@@ -548,18 +562,18 @@ extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const f
     if (C <= 256) {
         const int rpw = 8;  // 8 * 2 rows per warp
         const int rows_per_block = 8 * rpw * 2;
-        layernorm_kernel<16, 4><<<(M + rows_per_block - 1) / rows_per_block, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+        SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<16, 4>, (M + rows_per_block - 1) / rows_per_block, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
     } else {
         // register footprint follows the row length (float4 per lane): 3 for C <= 384, 5 for C <= 640, else 9
         const int rpw = 4;
         const int rows_per_block = 8 * rpw;
         const unsigned grid = (M + rows_per_block - 1) / rows_per_block;
         if (C <= 384)
-            layernorm_kernel<32, 3><<<grid, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 3>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
         else if (C <= 640)
-            layernorm_kernel<32, 5><<<grid, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 5>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
         else
-            layernorm_kernel<32, 9><<<grid, 256, 0, st>>>(x, gamma, beta, yo, M, C, eps, rpw);
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 9>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
     }
     SPG_LAUNCHED();
     return SPG_OK;
@@ -570,7 +584,7 @@ extern "C" int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_
     SPG_CHECK_ARG(B > 0 && S > 0 && S % 4 == 0, "bad image size S=%d", S);
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
     const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * 21;
-    patchify_kernel<<<capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(cols), B, S);
+    SPG_CHECK_CUDA((launch_pdl(patchify_kernel, capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), x, static_cast<uint4*>(cols), B, S)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -579,8 +593,7 @@ extern "C" int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W,
     SPG_CHECK_ARG(x && y, "null pointer");
     SPG_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool needs even H, W and C %% 4 == 0");
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 4);
-    maxpool_kernel<<<capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), B, H, W, C / 4);
+    SPG_CHECK_CUDA((launch_pdl(maxpool_kernel, capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), B, H, W, C / 4)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -588,8 +601,7 @@ extern "C" int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W,
 extern "C" int spg_cast_f32_h16(const float* x, void* y, long long n, spg_stream_t stream) {
     SPG_CHECK_ARG(x && y, "null pointer");
     SPG_CHECK_ARG(n > 0 && n % 8 == 0, "cast needs n %% 8 == 0");
-    cast_kernel<<<capped_blocks(n / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4*>(x), static_cast<uint4*>(y), n / 8);
+    SPG_CHECK_CUDA((launch_pdl(cast_kernel, capped_blocks(n / 8), 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(x), static_cast<uint4*>(y), n / 8)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -603,9 +615,8 @@ extern "C" int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0,
     SPG_CHECK_ARG(Ho % h0 == 0 && Ho / h0 >= 2 && Wo % w0 == 0 && Wo / w0 >= 2, "src0 must be upsampled by an integer factor >= 2");
     SPG_CHECK_ARG(c1 == 0 || (Ho % h1 == 0 && Ho / h1 >= 2 && Wo % w1 == 0 && Wo / w1 >= 2),
                   "src1 must be upsampled by an integer factor >= 2");
-    upcat_kernel<<<dim3(Ho / 2, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(src0), h0, w0, c0 / 8, static_cast<const uint4*>(src1), h1, w1, c1 / 8,
-        static_cast<uint4*>(out), Ho, Wo);
+    SPG_CHECK_CUDA((launch_pdl(upcat_kernel, dim3(Ho / 2, B), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(src0), h0, w0, c0 / 8, static_cast<const uint4*>(src1), h1, w1, c1 / 8,
+        static_cast<uint4*>(out), Ho, Wo)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -614,9 +625,8 @@ extern "C" int spg_fusion_combine(const float* g2, const float* g3, const float*
                                   float* row_sums, int B, int Hs, int C, spg_stream_t stream) {
     SPG_CHECK_ARG(g2 && g3 && g4 && bias && fused && row_sums, "null pointer");
     SPG_CHECK_ARG(Hs % 4 == 0 && C % 4 == 0, "fusion_combine needs Hs %% 4 == 0 and C %% 4 == 0");
-    fusion_combine_kernel<<<dim3(Hs, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4*>(g2), reinterpret_cast<const float4*>(g3), reinterpret_cast<const float4*>(g4),
-        reinterpret_cast<const float4*>(bias), static_cast<uint2*>(fused), reinterpret_cast<float4*>(row_sums), Hs, C / 4);
+    SPG_CHECK_CUDA((launch_pdl(fusion_combine_kernel, dim3(Hs, B), 128, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(g2), reinterpret_cast<const float4*>(g3), reinterpret_cast<const float4*>(g4),
+        reinterpret_cast<const float4*>(bias), static_cast<uint2*>(fused), reinterpret_cast<float4*>(row_sums), Hs, C / 4)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -624,8 +634,7 @@ extern "C" int spg_fusion_combine(const float* g2, const float* g3, const float*
 extern "C" int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C, spg_stream_t stream) {
     SPG_CHECK_ARG(x && row_sums, "null pointer");
     SPG_CHECK_ARG(C % 4 == 0, "row_sums needs C %% 4 == 0");
-    row_sums_kernel<<<dim3(H, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint2*>(x), reinterpret_cast<float4*>(row_sums), H, W, C / 4);
+    SPG_CHECK_CUDA((launch_pdl(row_sums_kernel, dim3(H, B), 128, 0, static_cast<cudaStream_t>(stream), static_cast<const uint2*>(x), reinterpret_cast<float4*>(row_sums), H, W, C / 4)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -634,8 +643,7 @@ extern "C" int spg_pooled_mlp(const float* row_sums, int rows, int count, const 
                               const float* W2, float* out, int B, int C, spg_stream_t stream) {
     SPG_CHECK_ARG(row_sums && W1 && out, "null pointer");
     SPG_CHECK_ARG(rows > 0 && count > 0 && R > 0 && C > 0, "bad pooled_mlp shape");
-    pooled_mlp_kernel<<<B, 512, (C + R) * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-        row_sums, rows, 1.0f / count, W1, b1, R, W2, out, C);
+    SPG_CHECK_CUDA((launch_pdl(pooled_mlp_kernel, B, 512, (C + R) * sizeof(float), static_cast<cudaStream_t>(stream), row_sums, rows, 1.0f / count, W1, b1, R, W2, out, C)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -644,8 +652,7 @@ extern "C" int spg_scale_channels_h16(void* x, const float* gate, int B, int HW,
     SPG_CHECK_ARG(x && gate, "null pointer");
     SPG_CHECK_ARG(C % 8 == 0, "scale_channels needs C %% 8 == 0");
     const long long total = static_cast<long long>(B) * HW * (C / 8);
-    scale_channels_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<uint4*>(x), gate, total, HW, C / 8);
+    SPG_CHECK_CUDA((launch_pdl(scale_channels_kernel, blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<uint4*>(x), gate, total, HW, C / 8)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -657,7 +664,7 @@ extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* d
     AsppParams p{static_cast<const uint4*>(x), dw, dw_bias, gvec, wf, wf_bias, static_cast<uint4*>(y), B, H, W,
                  {dilations[0], dilations[1], dilations[2], dilations[3]}};
     const long long total = static_cast<long long>(B) * H * W * 16;
-    aspp_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+    SPG_CHECK_CUDA((launch_pdl(aspp_kernel, blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream), p)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -670,14 +677,14 @@ extern "C" int spg_mask_stats_u8(const float* logits, const unsigned char* gt, u
     SPG_CHECK_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * 8 * sizeof(unsigned), st));
     if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(gt) & 3) ||
         (reinterpret_cast<uintptr_t>(mask) & 3)) {
-        mask_stats_scalar_kernel<<<dim3(min(64, (HW + 255) / 256), B), 256, 0, st>>>(logits, gt, mask, stats, HW, double_sigmoid);
+        SPG_CHECK_CUDA((launch_pdl(mask_stats_scalar_kernel, dim3(min(64, (HW + 255) / 256), B), 256, 0, st, logits, gt, mask, stats, HW, double_sigmoid)));
         SPG_LAUNCHED();
         return SPG_OK;
     }
     const int per_img = min(64, (HW / 4 + 255) / 256);
-    mask_stats_kernel<<<dim3(per_img, B), 256, 0, st>>>(reinterpret_cast<const float4*>(logits),
+    SPG_CHECK_CUDA((launch_pdl(mask_stats_kernel, dim3(per_img, B), 256, 0, st, reinterpret_cast<const float4*>(logits),
                                                         reinterpret_cast<const uchar4*>(gt),
-                                                        reinterpret_cast<uchar4*>(mask), stats, HW / 4, double_sigmoid);
+                                                        reinterpret_cast<uchar4*>(mask), stats, HW / 4, double_sigmoid)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -686,8 +693,7 @@ extern "C" int spg_up2_border_gather_h16(const void* x, void* out, int B, int H,
     SPG_CHECK_ARG(x && out, "null pointer");
     SPG_CHECK_ARG(B > 0 && H >= 2 && W >= 2 && C % 8 == 0, "bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
     const long long total = 2ll * B * H * 9 * (C / 8);
-    up2_border_gather_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint4*>(x), static_cast<uint4*>(out), B, H, W, C / 8);
+    SPG_CHECK_CUDA((launch_pdl(up2_border_gather_kernel, blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(x), static_cast<uint4*>(out), B, H, W, C / 8)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -695,8 +701,7 @@ extern "C" int spg_up2_border_gather_h16(const void* x, void* out, int B, int H,
 extern "C" int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream) {
     SPG_CHECK_ARG(x && y, "null pointer");
     const long long total = static_cast<long long>(B) * HW * C;
-    nhwc_to_nchw_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint16_t*>(x), y, HW, C, total);
+    SPG_CHECK_CUDA((launch_pdl(nhwc_to_nchw_kernel, blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(x), y, HW, C, total)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
