@@ -559,16 +559,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // Tile width.  256-wide tiles run the tensor pipe ~15 % faster than 192-wide ones (measured 1347 vs 1150 TFLOP/s at
 // long K), so when N is not a multiple of 256 but the padding of a ragged last tile costs <= 12 % (N = 1728, 3456,
 // 1152: 3.7 / 3.7 / 11 %) the launch uses 256-wide tiles with a ragged tail; otherwise the largest divisor of N.
-int pick_block_n(int N) {
+int pick_block_n(int N, int num_m_tiles = 1 << 20) {
     static const int ragged_env = [] { const char* e = getenv("SPG_GEMM_RAGGED"); return e ? atoi(e) : 1; }();
-    if (ragged_env && N > 256 && N % 256 != 0 && N % 64 == 0) {
+    static const int small_env0 = [] { const char* e = getenv("SPG_GEMM_SMALLM"); return e ? atoi(e) : 1; }();
+    const bool small = small_env0 && num_m_tiles * ((N + 255) / 256) * 2 <= sm_count();
+    if (ragged_env && !small && N > 256 && N % 256 != 0 && N % 64 == 0) {
         const int padded = (N + 255) / 256 * 256;
         if ((padded - N) * 100 <= 12 * N) return 256;
     }
     static const int max_bn_env = [] { const char* e = getenv("SPG_GEMM_MAX_BN"); return e ? atoi(e) : 256; }();  // tuning
+    int best = 0;
     for (int bn = max_bn_env; bn >= 16; bn -= 16)
-        if (N % bn == 0) return bn;
-    return 0;
+        if (N % bn == 0) {
+            best = bn;
+            break;
+        }
+    // Small problems (batch 1: M = 1024 / 256 rows in stages 3 / 4) fill less than half of the SMs with the widest
+    // tile, and a tile's time is then set by the TMA round trips of its k-loop rather than by its width: take the
+    // narrowest tile (>= 64 columns) that still fits one wave, i.e. the most CTAs working in parallel.
+    static const int small_env = [] { const char* e = getenv("SPG_GEMM_SMALLM"); return e ? atoi(e) : 1; }();
+    if (small_env && best > 64 && num_m_tiles * ((N + best - 1) / best) * 2 <= sm_count()) {
+        for (int bn = 64; bn < best; bn += 16)
+            if (N % bn == 0 && num_m_tiles * (N / bn) <= sm_count()) return bn;
+    }
+    return best;
 }
 
 // CTA pairs (cta_group::2).  Must be decided before the weight tensor map is encoded: in pair mode each CTA's
@@ -729,8 +743,8 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     EpiMaps em;
     a.M = M;
     a.N = N;
-    a.block_n = pick_block_n(N);
     a.num_m_tiles = (M + kBlockM - 1) / kBlockM;
+    a.block_n = pick_block_n(N, a.num_m_tiles);
     a.num_n_tiles = (N + a.block_n - 1) / a.block_n;
     a.num_k_chunks = (K + kBlockK - 1) / kBlockK;
     a.conv = 0;
