@@ -559,13 +559,18 @@ extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const f
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     uint16_t* yo = static_cast<uint16_t*>(y);
     // rows per warp so that one block (8 warps) streams roughly 64 KB+ and the grid stays far below the block-launch rate
+    // small M (batch 1): fewer rows per warp so that the grid still covers the machine
+    auto fit = [&](int rpw, int rows_per_iter) {
+        while (rpw > 1 && (M + 8 * rpw * rows_per_iter - 1) / (8 * rpw * rows_per_iter) < 2 * sm_count()) rpw >>= 1;
+        return rpw;
+    };
     if (C <= 256) {
-        const int rpw = 8;  // 8 * 2 rows per warp
+        const int rpw = fit(8, 2);  // 8 * 2 rows per warp
         const int rows_per_block = 8 * rpw * 2;
         SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<16, 4>, (M + rows_per_block - 1) / rows_per_block, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
     } else {
         // register footprint follows the row length (float4 per lane): 3 for C <= 384, 5 for C <= 640, else 9
-        const int rpw = 4;
+        const int rpw = fit(4, 1);
         const int rows_per_block = 8 * rpw;
         const unsigned grid = (M + rows_per_block - 1) / rows_per_block;
         if (C <= 384)

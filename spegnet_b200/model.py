@@ -174,7 +174,7 @@ class _Workspace:
 class SPEGNet(nn.Module):
     """B200-native SPEGNet (inference).  See module docstring for the contract."""
 
-    def __init__(self, config: Dict, compute_dtype: Optional[torch.dtype] = None, cuda_graph_max_batch: int = 4):
+    def __init__(self, config: Dict, compute_dtype: Optional[torch.dtype] = None, cuda_graph_max_batch: int = 8):
         super().__init__()
         # Batches up to this size replay a captured CUDA graph of the ~370-launch forward (launch overhead
         # otherwise dominates batch-1 latency); 0 disables.  Larger batches are GPU-bound and launch eagerly.
