@@ -51,6 +51,10 @@ const char* spg_last_error(void);
 int spg_device_check(void);
 /* 1 if this build stores activations / weights as IEEE fp16, 0 if bfloat16. */
 int spg_half_is_fp16(void);
+/* Programmatic dependent launch for the kernels enqueued from now on (1 = on, the default): every kernel then carries
+ * cudaLaunchAttributeProgrammaticStreamSerialization and overlaps its global-data-free prologue with the tail of its
+ * predecessor (griddepcontrol.launch_dependents / wait).  The environment variable SPG_PDL=0|1 overrides it. */
+void spg_set_pdl(int on);
 /* Number of kernels this library has launched since load / since the last reset (all threads). */
 long long spg_launch_count(void);
 void spg_launch_count_reset(void);

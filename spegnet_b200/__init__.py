@@ -4,6 +4,7 @@
 ``ops`` exposes the individual C-ABI kernels; ``_lib`` is the ctypes binding of libspegnet_b200.so.
 """
 from .model import SPEGNet  # noqa: F401
+from .pipeline import HostPipeline  # noqa: F401
 
-__all__ = ["SPEGNet"]
+__all__ = ["SPEGNet", "HostPipeline"]
 __version__ = "0.1.0"

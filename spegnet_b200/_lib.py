@@ -66,6 +66,7 @@ _SPECIAL = {
     "spg_last_error": ([], C.c_char_p),
     "spg_launch_count": ([], C.c_longlong),
     "spg_launch_count_reset": ([], None),
+    "spg_set_pdl": ([_I], None),
     "spg_sod_workspace_bytes": ([_I, _I, _I], C.c_size_t),
     "spg_preprocess_workspace_bytes": ([_I, _I, _I], C.c_size_t),
 }
@@ -127,6 +128,12 @@ def check(rc: int, what: str, dtype: str = DEFAULT_DTYPE) -> None:
         if rc == -1:
             raise ValueError(f"{what}: {msg}")
         raise SpgError(f"{what} failed (code {rc}): {msg}")
+
+
+def set_pdl(on: bool) -> None:
+    """Programmatic dependent launch on / off for every loaded library variant (see spg_set_pdl)."""
+    for lib in _libs.values():
+        lib.spg_set_pdl(int(bool(on)))
 
 
 def launch_count() -> int:

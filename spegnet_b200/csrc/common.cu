@@ -37,9 +37,13 @@ int sm_count() {
     return cached;
 }
 
+// SPG_PDL=0 / 1 pins the switch; otherwise the host sets it per forward (spg_set_pdl): on in the latency regime
+// (small batches, where the launch / prologue / tail of 371 kernels is a third of the time), off for large batches,
+// where it measured neutral on the device-timed step and -3 % end to end with copy streams active.
+static std::atomic<int> g_pdl{1};
 bool pdl_enabled() {
-    static const bool on = [] { const char* e = getenv("SPG_PDL"); return e == nullptr || atoi(e) != 0; }();
-    return on;
+    static const int pinned = [] { const char* e = getenv("SPG_PDL"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
+    return pinned >= 0 ? pinned != 0 : g_pdl.load(std::memory_order_relaxed) != 0;
 }
 
 namespace {
@@ -164,6 +168,8 @@ extern "C" int spg_device_check(void) {
     if (major != 10) return spg::fail(SPG_ERR_UNSUPPORTED, "device is sm_%d%d; this library is sm_100a only", major, minor);
     return SPG_OK;
 }
+
+extern "C" void spg_set_pdl(int on) { spg::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 extern "C" long long spg_launch_count(void) { return spg::g_launches.load(std::memory_order_relaxed); }
 extern "C" void spg_launch_count_reset(void) { spg::g_launches.store(0, std::memory_order_relaxed); }

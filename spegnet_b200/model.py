@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import _lib, ops
 from .schema import (ASPP_DILATIONS, BN_EPS, LN_EPS, VARIANT_CHANNELS, TrunkSpec, head_entries, trunk_blocks,
                      trunk_param_shapes)
 
@@ -356,6 +356,8 @@ class SPEGNet(nn.Module):
         if self._packed is None:
             self._packed = self._pack()
         x = x.contiguous().float()
+        # programmatic dependent launch pays in the latency regime only (DESIGN.md "Measurement")
+        _lib.set_pdl(B <= max(self.cuda_graph_max_batch, 8))
         if 0 < B <= self.cuda_graph_max_batch and self._debug_taps is None and not torch.cuda.is_current_stream_capturing():
             return self._forward_graphed(x, B, S)
         return self._forward_eager(x, B, S)

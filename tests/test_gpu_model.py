@@ -205,3 +205,24 @@ def test_launches_are_counted_and_native(model_fp16):
         model_fp16(_images(1, 256).cuda())
     torch.cuda.synchronize()
     assert _lib.launch_count() >= 350  # 48 blocks x 7-9 kernels + head, all from libspegnet_b200_fp16.so
+
+
+def test_host_pipeline_returns_the_forward_results_in_order(spread_sd):
+    """HostPipeline (copies on their own streams, ring of two buffers) must hand back exactly what the plain
+    `model(x.cuda())` call produces, batch by batch, including a ragged last batch."""
+    from spegnet_b200 import HostPipeline, SPEGNet
+
+    model = SPEGNet({"encoder": {"config_path": "", "checkpoint_path": "", "variant": "large"}})
+    model.load_state_dict(spread_sd)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(21)
+    batches = [torch.randn(b, 3, 256, 256, generator=g).pin_memory() for b in (2, 2, 2, 2, 1)]
+    want = []
+    with torch.no_grad():
+        for x in batches:
+            out = model(x.cuda())
+            want.append((out["predictions"][-1].cpu(), out["edge"].cpu()))
+    got = [(o["prediction"].clone(), o["edge"].clone()) for o in HostPipeline(model).run(batches)]
+    assert len(got) == len(want)
+    for (gp, ge), (wp, we) in zip(got, want):
+        assert torch.equal(gp, wp) and torch.equal(ge, we)
