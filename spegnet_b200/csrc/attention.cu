@@ -36,6 +36,7 @@ struct AttnParams {
     int wpc;     // windows per CTA (Nq < 64) else 1
     int qtiles;  // 64-row query tiles per window (Nq >= 64) else 1
     int box_h;   // window rows per K/V TMA box (box = 72 ch x ws x box_h tokens, <= 256 tokens)
+    int rows_smem;  // key rows staged per pass = min(256, keys this CTA sees): sizes the dynamic shared memory
     float scale_log2e;
 };
 
@@ -81,7 +82,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
     // the first QK^T tiles start while the rest of the window is still in flight
     __shared__ __align__(8) uint64_t kv_bar[4];
     const uint32_t Ks_u = (smem_u32(smem) + 127u) & ~127u;  // TMA destinations: 128-byte aligned
-    const uint32_t Vs_u = Ks_u + kRowsSmem * kHd * 2;
+    const uint32_t Vs_u = Ks_u + p.rows_smem * kHd * 2;
     const uint32_t bar_u = smem_u32(&kv_bar[0]);
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_kv);
@@ -401,11 +402,16 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     SPG_CHECK_ARG(ws <= 64 && p.box_h >= 1, "window %d too wide for the K/V staging", ws);
     CUtensorMap tmap;
     if (int rc = make_tmap_qkv_window(&tmap, qkv, B, H, W, 3 * D, kHd, ws, p.box_h)) return rc;
-    const int smem = 2 * kRowsSmem * kHd * 2 + 128;
+    // stage only what a CTA consumes per pass (64 keys = 18 KB of K + V for the small windows).  Occupancy is then set
+    // by registers (135 -> 3 CTAs / SM); capping them at 128 for a 4th CTA spills and measured slower (global blocks
+    // 600 -> 710 us), so the kernel keeps its natural register count
+    p.rows_smem = (p.wpc > 1 ? p.wpc * p.Nk : p.Nk) < kRowsSmem ? (p.wpc > 1 ? p.wpc * p.Nk : p.Nk) : kRowsSmem;
+    const int smem = 2 * p.rows_smem * kHd * 2 + 128;
     static bool attr_set = false;
     if (!attr_set) {
-        SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int smem_max = 2 * kRowsSmem * kHd * 2 + 128;
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         attr_set = true;
     }
     dim3 grid(p.wpc > 1 ? nwin / p.wpc : nwin * p.qtiles, heads);
