@@ -25,6 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION in this image) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 GFLOP_PER_IMAGE = {512: 610.98, 1024: 2530.89}  # algorithmic, reference formulation
 # DRAM traffic of one launch of the dominant kernel from an `ncu --set full` capture (profiles/
