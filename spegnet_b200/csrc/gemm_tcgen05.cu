@@ -62,6 +62,7 @@ struct GemmArgs {
     int block_n;
     int num_m_tiles, num_n_tiles, num_k_chunks;
     int stages;
+    int l2_prefetch; // linear mode: prefetch the next tile's A rows into L2 one tile ahead
     int pair;        // launch as CTA pairs (cta_group::2): decided on the host, selects the kPair kernel instance
     int halo;        // conv only: one stage = a 130-pixel halo row of A + the 3 dx-tap weight tiles (A reuse x3)
     // conv mode
@@ -209,6 +210,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const int rem = m0 - img * hw;
                     y0 = rem / p.W;
                     x0 = rem - y0 * p.W;
+                }
+                // The first touch of an m-block's A rows comes from HBM (the weights and every later n-tile hit L2), and the
+                // ring only looks `stages` k-chunks (~1.5 us) ahead: each tile would start with an HBM-latency bubble
+                // (measured as a fixed ~1.6 us per tile, which is what separates K = 576 from long-K efficiency).  So the
+                // A rows of this CTA's NEXT tile are prefetched into L2 now, one whole tile ahead; the CTAs working on the
+                // same m-block share the job (chunk kc goes to the CTA whose n-block is kc mod #n-tiles).
+                if (p.l2_prefetch) {
+                    const int nt = tile + nunits;
+                    if (nt < total_tiles) {
+                        const int nm_unit = nt / p.num_n_tiles;
+                        const int nn_blk = nt - nm_unit * p.num_n_tiles;
+                        const int nm_blk = kPair ? 2 * nm_unit + static_cast<int>(rank) : nm_unit;
+                        for (int kc = nn_blk; kc < p.num_k_chunks; kc += p.num_n_tiles)
+                            tma_prefetch_l2_2d(&tmap_a, kc * kBlockK, nm_blk * kBlockM);
+                    }
                 }
                 // kUp2: the tile is part of one image row; rows 0 / H-1 use their own weight sets (stacked along N)
                 const int w_row0 = kUp2 ? (y0 == 0 ? 0 : (y0 == p.H - 1 ? 2 * p.N : p.N)) : 0;
@@ -753,6 +769,10 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.tile_w = 1;
     if (int rc = fill_epilogue(a, em, ep, M, N)) return rc;
     decide_pair(a);
+    static const int l2pf_env = [] { const char* e = getenv("SPG_GEMM_L2PF"); return e ? atoi(e) : 1; }();
+    // pays on short reductions without a residual stream (fc1 +3.5 %, QKV +2 %); with K = 2304 and an fp32 residual
+    // in flight the extra requests cost 9 %
+    a.l2_prefetch = l2pf_env && !a.has_res && a.num_k_chunks <= 18 && a.num_m_tiles * a.num_n_tiles > 2 * sm_count() ? 1 : 0;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(K) * 2, kBlockM)) return rc;
     if (int rc = make_tmap_2d(&tb, W, N, K, static_cast<uint64_t>(K) * 2, a.pair ? a.block_n / 2 : a.block_n)) return rc;
