@@ -92,6 +92,19 @@ struct GemmArgs {
     float* head_out;
 };
 
+#ifdef SPG_TRACE
+// Timeline instrumentation (variant builds only: tools/build_variant.sh trace -DSPG_TRACE): SM-clock stamps of CTA 0's
+// producer / MMA issuer / epilogue warp 2 for its first 64 tiles + the cycles the issuer spent waiting for operands,
+// dumped by spg_debug_trace_dump (tests/cuda/test_gemm.cu --shape prints them).  profiles/r01_gemm_timeline.md.
+__device__ long long g_trace[64 * 12];
+#define SPG_STAMP(tile_i, slot)                                                           \
+    do {                                                                                  \
+        if (blockIdx.x == 0 && (tile_i) < 64) g_trace[(tile_i) * 12 + (slot)] = clock64(); \
+    } while (0)
+#else
+#define SPG_STAMP(tile_i, slot) do {} while (0)
+#endif
+
 // Exact-erf GELU without libdevice erff (which costs ~4x the issue slots because both of its branches are
 // predicated).  With Phi the normal CDF, gelu(x) = x Phi(x) = max(x, 0) - |x| (1 - Phi(|x|)) and
 //   1 - Phi(t) = erfc(t / sqrt 2) / 2 = 2^P(t),   P = degree-4 fit of log2(erfc(t / sqrt 2)) - 1 on [0, 5.65] that
@@ -199,7 +212,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int hw = p.H * p.W;
             // pair mode: both CTAs load; all transaction bytes are signalled on the leader's full barrier
             const uint32_t n_half = kPair ? rank * (p.block_n / 2) : 0u;  // this CTA's slice of the weight tile
-            for (int tile = unit; tile < total_tiles; tile += nunits) {
+            [[maybe_unused]] int trace_i = 0;
+            for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
+                SPG_STAMP(trace_i, 0);
                 const int m_unit = tile / p.num_n_tiles;
                 const int n_blk = tile - m_unit * p.num_n_tiles;
                 const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;  // this CTA's 128-row block
@@ -272,6 +287,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         phase ^= 1u;
                     }
                 }
+                SPG_STAMP(trace_i, 1);
             }
         }
     } else if (warp == 1) {
@@ -290,13 +306,26 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = unit; tile < total_tiles; tile += nunits) {
+            [[maybe_unused]] int trace_i = 0;
+            for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
+                SPG_STAMP(trace_i, 2);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
+                SPG_STAMP(trace_i, 3);
                 const uint32_t d_tmem = tmem_base + acc * kAccStageCols;
+#ifdef SPG_TRACE
+                long long starved = 0;
+#endif
                 for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+#ifdef SPG_TRACE
+                    const long long w0 = clock64();
+#endif
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
+#ifdef SPG_TRACE
+                    if (kc > 0) starved += clock64() - w0;  // cycles the issuer waited for operands (first chunk excluded)
+                    if (kc == 0) SPG_STAMP(trace_i, 4);
+#endif
                     const uint32_t a_addr = tiles_addr + stage * stage_bytes;
                     if (p.halo) {
                         // tap dx reads the same halo rows shifted by dx pixels: start address + dx * 128 B.  The 128 B
@@ -330,6 +359,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                 }
                 commit(tmem_full_bar(acc));
+                SPG_STAMP(trace_i, 5);
+#ifdef SPG_TRACE
+                if (blockIdx.x == 0 && trace_i < 64) g_trace[trace_i * 12 + 10] = starved;
+#endif
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -366,7 +399,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         uint32_t res_parity = 0;
         // the accumulator stage is handed back on the LEADER's tmem_empty barrier (the leader issues the MMAs)
         const uint32_t tmem_empty_remote0 = kPair ? mapa_shared(tmem_empty_bar(0), 0) : 0u;
-        for (int tile = unit; tile < total_tiles; tile += nunits) {
+        [[maybe_unused]] int trace_i = 0;
+        for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
+            if (ewarp == 0 && lane == 0) SPG_STAMP(trace_i, 6);
             const int m_unit = tile / p.num_n_tiles;
             const int n_blk = tile - m_unit * p.num_n_tiles;
             const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;
@@ -416,8 +451,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // bias staged (double-buffered across tiles)
 
+            if (ewarp == 0 && lane == 0) SPG_STAMP(trace_i, 7);
             mbar_wait(tmem_full_bar(acc), acc_phase);
             tc_fence_after();
+            if (ewarp == 0 && lane == 0) SPG_STAMP(trace_i, 8);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStageCols;
             const int row = row0 + lane;
             const bool row_ok = row < p.M;
@@ -539,6 +576,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
             }
             // accumulator fully read: hand the TMEM stage back to the MMA warp
+            if (ewarp == 0 && lane == 0) SPG_STAMP(trace_i, 9);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -862,3 +900,12 @@ extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const flo
     if (int rc = make_tmap_2d(&tb, w_phase, 3ull * a.N, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;
     return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
 }
+
+#ifdef SPG_TRACE
+extern "C" int spg_debug_trace_dump(long long* host, int n) {
+    using namespace spg;
+    SPG_CHECK_CUDA(cudaDeviceSynchronize());
+    SPG_CHECK_CUDA(cudaMemcpyFromSymbol(host, g_trace, sizeof(long long) * (n < 64 * 12 ? n : 64 * 12)));
+    return SPG_OK;
+}
+#endif

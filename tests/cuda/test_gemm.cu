@@ -13,6 +13,9 @@
 #include <cuda_runtime.h>
 
 #include "../../include/spegnet_b200.h"
+#ifdef SPG_TRACE
+extern "C" int spg_debug_trace_dump(long long*, int);
+#endif
 
 #define CK(x)                                                                          \
     do {                                                                               \
@@ -290,6 +293,19 @@ int main(int argc, char** argv) {
             g_check = false;
             case_gemm(atoi(argv[i + 1]), atoi(argv[i + 2]), atoi(argv[i + 3]), atoi(argv[i + 4]), true, atoi(argv[i + 5]) != 0, 0,
                       atoi(argv[i + 6]) != 0, false);
+#ifdef SPG_TRACE
+            {   // SM-clock timeline of CTA 0 (last launch): producer / MMA issuer / epilogue warp 2 per tile
+                static long long tr[64 * 12];
+                spg_debug_trace_dump(tr, 64 * 12);
+                const long long t0 = tr[0];
+                printf("tile | prod start, prod issued | mma start, acc free, first chunk landed, all issued | epi start, bias staged, acc full, acc read | issuer waited   (SM cycles since CTA start)\n");
+                for (int t = 0; t < 24; ++t) {
+                    printf("%4d |", t);
+                    for (int k = 0; k < 10; ++k) printf(" %8lld%s", tr[t * 12 + k] - t0, (k == 1 || k == 5) ? " |" : "");
+                    printf(" | %lld\n", tr[t * 12 + 10]);
+                }
+            }
+#endif
             return g_fail;
         }
     }

@@ -12,5 +12,5 @@ for f in *.cu; do
 done
 wait
 nvcc $ARCH -shared -o $out/libspegnet_b200_fp16.so $out/*.o -cudart shared
-nvcc $ARCH -O2 -std=c++17 -DSPG_FP16 -o $out/test_gemm ../../tests/cuda/test_gemm.cu -L$out -lspegnet_b200_fp16 -Xlinker -rpath -Xlinker '$ORIGIN' -cudart shared
+nvcc $ARCH -O2 -std=c++17 -DSPG_FP16 "$@" -o $out/test_gemm ../../tests/cuda/test_gemm.cu -L$out -lspegnet_b200_fp16 -Xlinker -rpath -Xlinker '$ORIGIN' -cudart shared
 echo built $out
