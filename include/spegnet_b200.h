@@ -55,6 +55,9 @@ int spg_half_is_fp16(void);
  * cudaLaunchAttributeProgrammaticStreamSerialization and overlaps its global-data-free prologue with the tail of its
  * predecessor (griddepcontrol.launch_dependents / wait).  The environment variable SPG_PDL=0|1 overrides it. */
 void spg_set_pdl(int on);
+/* Traversal direction of the kernels enqueued from now on (0 = ascending rows / tiles, 1 = descending).  The host
+ * alternates it launch by launch so that each consumer starts on the rows its producer wrote last (still in L2). */
+void spg_set_reverse(int reversed);
 /* Number of kernels this library has launched since load / since the last reset (all threads). */
 long long spg_launch_count(void);
 void spg_launch_count_reset(void);

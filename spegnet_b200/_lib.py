@@ -67,6 +67,7 @@ _SPECIAL = {
     "spg_launch_count": ([], C.c_longlong),
     "spg_launch_count_reset": ([], None),
     "spg_set_pdl": ([_I], None),
+    "spg_set_reverse": ([_I], None),
     "spg_sod_workspace_bytes": ([_I, _I, _I], C.c_size_t),
     "spg_preprocess_workspace_bytes": ([_I, _I, _I], C.c_size_t),
 }
@@ -134,6 +135,19 @@ def set_pdl(on: bool) -> None:
     """Programmatic dependent launch on / off for every loaded library variant (see spg_set_pdl)."""
     for lib in _libs.values():
         lib.spg_set_pdl(int(bool(on)))
+
+
+_direction = 0
+
+
+def flip_direction() -> None:
+    """Alternate the traversal direction for the next launch (see spg_set_reverse); SPG_SNAKE=0 keeps it ascending."""
+    global _direction
+    if os.environ.get("SPG_SNAKE", "1") == "0":
+        return
+    _direction ^= 1
+    for lib in _libs.values():
+        lib.spg_set_reverse(_direction)
 
 
 def launch_count() -> int:

@@ -36,6 +36,7 @@ struct AttnParams {
     int wpc;     // windows per CTA (Nq < 64) else 1
     int qtiles;  // 64-row query tiles per window (Nq >= 64) else 1
     int box_h;   // window rows per K/V TMA box (box = 72 ch x ws x box_h tokens, <= 256 tokens)
+    int reverse;    // walk the window groups in descending order (common.h "Traversal direction")
     int rows_smem;  // key rows staged per pass = min(256, keys this CTA sees): sizes the dynamic shared memory
     float scale_log2e;
 };
@@ -99,13 +100,14 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
     const int wins_per_img = p.nwx * p.nwy;
 
     // ---- which windows / query rows this CTA owns
+    const int blk = p.reverse ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
     int win0, qt;
     if (p.wpc > 1) {
-        win0 = blockIdx.x * p.wpc;
+        win0 = blk * p.wpc;
         qt = 0;
     } else {
-        win0 = blockIdx.x / p.qtiles;
-        qt = blockIdx.x - win0 * p.qtiles;
+        win0 = blk / p.qtiles;
+        qt = blk - win0 * p.qtiles;
     }
     const int my_win = win0 + (p.wpc > 1 ? warp : 0);
     const int b = my_win / wins_per_img;
@@ -383,6 +385,7 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     p.Nk = ws * ws;
     p.Nq = q_pool ? p.Nk / 4 : p.Nk;
     p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
+    p.reverse = traversal_reversed() ? 1 : 0;
     const int nwin = B * p.nwx * p.nwy;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // tensor-core path: 64-row query tiles over <=256-key passes, or four 16-query windows per CTA

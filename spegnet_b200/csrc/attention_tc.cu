@@ -50,6 +50,7 @@ struct AttnTcParams {
     int B, H, W, D, heads;
     int nwx, nwy;
     int items;  // B * nwy * nwx * heads
+    int reverse;  // walk the items in descending order (common.h "Traversal direction")
     float scale_log2e;
 };
 
@@ -96,6 +97,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
 
     const int wins_per_img = p.nwx * p.nwy;
     auto decode = [&](int item, int& head, int& y0, int& x0) {
+        if (p.reverse) item = p.items - 1 - item;
         head = item % p.heads;
         const int win = item / p.heads;
         const int b = win / wins_per_img;
@@ -320,6 +322,7 @@ extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, in
     p.B = B; p.H = H; p.W = W; p.D = D; p.heads = heads;
     p.nwx = W / kWs; p.nwy = H / kWs;
     p.items = B * p.nwx * p.nwy * heads;
+    p.reverse = traversal_reversed() ? 1 : 0;
     p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
     CUtensorMap tmain, ttail;
     if (int rc = make_tmap_qkv_5d(&tmain, qkv, static_cast<uint64_t>(B) * H, W, heads, 64, kWs, 8, 128)) return rc;

@@ -169,6 +169,12 @@ extern "C" int spg_device_check(void) {
     return SPG_OK;
 }
 
+namespace spg {
+static std::atomic<int> g_reverse{0};
+bool traversal_reversed() { return g_reverse.load(std::memory_order_relaxed) != 0; }
+}  // namespace spg
+extern "C" void spg_set_reverse(int reversed) { spg::g_reverse.store(reversed ? 1 : 0, std::memory_order_relaxed); }
+
 extern "C" void spg_set_pdl(int on) { spg::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 extern "C" long long spg_launch_count(void) { return spg::g_launches.load(std::memory_order_relaxed); }

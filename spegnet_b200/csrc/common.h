@@ -78,6 +78,12 @@ int sm_count();
 // ---------------------------------------------------------------------------------------------------------------
 bool pdl_enabled();
 
+// Traversal direction of the NEXT launch (spg_set_reverse): consecutive kernels of the forward are producer ->
+// consumer pairs over tensors larger than the 126 MB L2, so a consumer that walks its rows in the OPPOSITE order of
+// its producer starts on the lines that are still resident.  The GEMM / conv engine, LayerNorm and the attention
+// kernels honour the flag (tile / block / item index i -> n-1-i); the host flips it before every launch.
+bool traversal_reversed();
+
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -62,6 +62,7 @@ struct GemmArgs {
     int block_n;
     int num_m_tiles, num_n_tiles, num_k_chunks;
     int stages;
+    int reverse;     // walk the tiles in descending order (see common.h "Traversal direction")
     int l2_prefetch; // linear mode: prefetch the next tile's A rows into L2 one tile ahead
     int pair;        // launch as CTA pairs (cta_group::2): decided on the host, selects the kPair kernel instance
     int halo;        // conv only: one stage = a 130-pixel halo row of A + the 3 dx-tap weight tiles (A reuse x3)
@@ -215,8 +216,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             [[maybe_unused]] int trace_i = 0;
             for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
                 SPG_STAMP(trace_i, 0);
-                const int m_unit = tile / p.num_n_tiles;
-                const int n_blk = tile - m_unit * p.num_n_tiles;
+                const int t_idx = p.reverse ? total_tiles - 1 - tile : tile;
+                const int m_unit = t_idx / p.num_n_tiles;
+                const int n_blk = t_idx - m_unit * p.num_n_tiles;
                 const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;  // this CTA's 128-row block
                 int img = 0, y0 = 0, x0 = 0;
                 if (p.conv) {
@@ -232,8 +234,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // A rows of this CTA's NEXT tile are prefetched into L2 now, one whole tile ahead; the CTAs working on the
                 // same m-block share the job (chunk kc goes to the CTA whose n-block is kc mod #n-tiles).
                 if (p.l2_prefetch) {
-                    const int nt = tile + nunits;
-                    if (nt < total_tiles) {
+                    const int nt_raw = tile + nunits;
+                    if (nt_raw < total_tiles) {
+                        const int nt = p.reverse ? total_tiles - 1 - nt_raw : nt_raw;
                         const int nm_unit = nt / p.num_n_tiles;
                         const int nn_blk = nt - nm_unit * p.num_n_tiles;
                         const int nm_blk = kPair ? 2 * nm_unit + static_cast<int>(rank) : nm_unit;
@@ -402,8 +405,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         [[maybe_unused]] int trace_i = 0;
         for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
             if (ewarp == 0 && lane == 0) SPG_STAMP(trace_i, 6);
-            const int m_unit = tile / p.num_n_tiles;
-            const int n_blk = tile - m_unit * p.num_n_tiles;
+            const int t_idx = p.reverse ? total_tiles - 1 - tile : tile;
+            const int m_unit = t_idx / p.num_n_tiles;
+            const int n_blk = t_idx - m_unit * p.num_n_tiles;
             const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;
             const int n0 = n_blk * p.block_n;
             // ragged last n-tile (N not a multiple of block_n): only the valid 16-column chunks are processed; the
@@ -661,6 +665,7 @@ struct EpiMaps {
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, cudaStream_t stream) {
     const int total_1cta = a.num_m_tiles * a.num_n_tiles;
     const bool pair = a.pair != 0;
+    a.reverse = traversal_reversed() ? 1 : 0;
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
     const int stage_bytes = a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128;
     const int staging = a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0;

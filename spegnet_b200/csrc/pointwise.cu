@@ -34,7 +34,7 @@ constexpr int kLnMaxC = 1152;
 template <int LPR, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, uint16_t* __restrict__ y,
-                                                        int M, int C, float eps, int rows_per_warp) {
+                                                        int M, int C, float eps, int rows_per_warp, int reverse) {
     pdl_prologue();
     constexpr int RPW = 32 / LPR;  // rows processed concurrently by one warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
     const int nvec = C >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
-    const long long first = (static_cast<long long>(blockIdx.x) * 8 + warp) * rows_per_warp * RPW;
+    const unsigned bid = reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x;  // see common.h "Traversal direction"
+    const long long first = (static_cast<long long>(bid) * 8 + warp) * rows_per_warp * RPW;
     for (int it = 0; it < rows_per_warp; ++it) {
         const long long row = first + it * RPW + grp;
         const bool ok = row < M;
@@ -606,18 +607,18 @@ extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const f
     if (C <= 256) {
         const int rpw = fit(8, 2);  // 8 * 2 rows per warp
         const int rows_per_block = 8 * rpw * 2;
-        SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<16, 4>, (M + rows_per_block - 1) / rows_per_block, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
+        SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<16, 4>, (M + rows_per_block - 1) / rows_per_block, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
     } else {
         // register footprint follows the row length (float4 per lane): 3 for C <= 384, 5 for C <= 640, else 9
         const int rpw = fit(4, 1);
         const int rows_per_block = 8 * rpw;
         const unsigned grid = (M + rows_per_block - 1) / rows_per_block;
         if (C <= 384)
-            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 3>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 3>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
         else if (C <= 640)
-            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 5>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 5>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
         else
-            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 9>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw)));
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 9>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
     }
     SPG_LAUNCHED();
     return SPG_OK;

@@ -69,6 +69,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bia
         raise ValueError(f"weight K {w.shape[1]} != activation K {K}")
     ep = _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out)
     lib, dn = _lib_for(a)
+    _lib.flip_direction()
     rc = lib.spg_linear_h16(_ptr(a, H16, "a"), _ptr(w, H16, "w"), M, N, K,
                                      C.byref(ep), _stream())
     _lib.check(rc, "spg_linear_h16", dn)
@@ -83,6 +84,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bi
         raise ValueError("conv weight must be [Cout, 9*Cin]")
     ep = _epilogue(out, bias, act, None, 0, head_w, head_b, head_out)
     lib, dn = _lib_for(x)
+    _lib.flip_direction()
     rc = lib.spg_conv3x3_h16(_ptr(x, H16, "x"), _ptr(w, H16, "w"), B, H, W, Cin, Cout,
                                       C.byref(ep), _stream())
     _lib.check(rc, "spg_conv3x3_h16", dn)
@@ -108,6 +110,7 @@ def conv3x3_up2(x: torch.Tensor, w_phase: torch.Tensor, corr: torch.Tensor, bias
     if tuple(out.shape) != (B, 2 * H, 2 * W, Cout) or tuple(corr.shape) != (2, B * H, 4 * Cout):
         raise ValueError("out / corr shape does not match x and w_phase")
     lib, dn = _lib_for(x)
+    _lib.flip_direction()
     rc = lib.spg_conv3x3_up2_h16(_ptr(x, H16, "x"), _ptr(w_phase, H16, "w_phase"), _ptr(corr, torch.float32, "corr"),
                                  B, H, W, Cin, Cout, _ptr(bias4, torch.float32, "bias4"), _ptr(out, H16, "out"), _stream())
     _lib.check(rc, "spg_conv3x3_up2_h16", dn)
@@ -116,6 +119,7 @@ def conv3x3_up2(x: torch.Tensor, w_phase: torch.Tensor, corr: torch.Tensor, bias
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, eps: float) -> None:
     M, Cc = x.shape
     lib, dn = _lib_for(y)
+    _lib.flip_direction()
     rc = lib.spg_layernorm_f32_h16(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
                                             _ptr(beta, torch.float32, "beta"), _ptr(y, H16, "y"), M, Cc,
                                             eps, _stream())
@@ -144,6 +148,7 @@ def cast_h16(x: torch.Tensor, y: torch.Tensor) -> None:
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, B: int, H: int, W: int, D: int, heads: int, window: int,
                      q_pool: bool) -> None:
     lib, dn = _lib_for(qkv)
+    _lib.flip_direction()
     rc = lib.spg_window_attention_h16(_ptr(qkv, H16, "qkv"), _ptr(out, H16, "out"), B,
                                                H, W, D, heads, window, int(q_pool), _stream())
     _lib.check(rc, "spg_window_attention_h16", dn)
