@@ -78,6 +78,24 @@ typedef struct spg_epilogue {
     const float* head_w;   /* [N] fp32 or NULL; needs N <= 256 and N % 16 == 0 */
     float head_b;
     float* head_out;       /* [M] fp32 */
+    /*
+     * LayerNorm folded into the GEMMs around it (blocks.{i}.norm1 / norm2, HF:modeling_sam2.py:495,528).  Every
+     * LayerNorm input of the trunk is the fp32 output of a residual GEMM and is read only by GEMMs, so:
+     *  - the PRODUCER (ln_emit_out != NULL, needs residual + fp32 out) also stores xc = out - c as a 16-bit copy, c =
+     *    the row's previous mean (from ln_prev_rec, 0 if NULL), and writes the row record ln_emit_rec[row][32] =
+     *    {c, P, (sum xc, sum xc^2) x P partials}: one partial per (n-tile, epilogue half), plain stores in fixed slots,
+     *    so the statistics are deterministic;
+     *  - the CONSUMER (ln_fold_rec != NULL) runs on A = xc with W' = W diag(gamma) and applies, per output row,
+     *    out = rstd * (acc - m * ln_fold_cw[n]) + bias[n]   (m, rstd from the record, over ln_cols channels; bias must
+     *    already contain W beta; ln_fold_cw[n] = sum_k W'[n,k]), then the activation.
+     */
+    const float* ln_fold_rec; /* consumer: [M][32] fp32 row records of A */
+    const float* ln_fold_cw;  /* consumer: [N] fp32 */
+    int ln_cols;              /* channels of the normalised row (consumer: K, producer: N) */
+    float ln_eps;
+    float* ln_emit_rec;       /* producer: [M][32] fp32 row records of out */
+    const float* ln_prev_rec; /* producer: records of the residual input rows, or NULL */
+    void* ln_emit_out;        /* producer: [M, N] 16-bit centred copy of out */
 } spg_epilogue_t;
 
 /*

@@ -29,6 +29,8 @@ class Epilogue(C.Structure):
         ("bias", C.c_void_p), ("act", C.c_int), ("residual", C.c_void_p), ("res_rows", C.c_int),
         ("out", C.c_void_p), ("out_dtype", C.c_int), ("head_w", C.c_void_p), ("head_b", C.c_float),
         ("head_out", C.c_void_p),
+        ("ln_fold_rec", C.c_void_p), ("ln_fold_cw", C.c_void_p), ("ln_cols", C.c_int), ("ln_eps", C.c_float),
+        ("ln_emit_rec", C.c_void_p), ("ln_prev_rec", C.c_void_p), ("ln_emit_out", C.c_void_p),
     ]
 
 

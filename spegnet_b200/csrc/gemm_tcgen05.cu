@@ -49,7 +49,9 @@ constexpr int kAccStageCols = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarBytes = 1024;                                // pipeline barriers + residual barriers
-constexpr int kEpiScratch = (2 * 256 + 256 + 3 * 128) * 4;      // bias[2][256], head weights[256], head partials[3][128]
+constexpr int kEpiScratch = (2 * 256 + 256 + 3 * 128 + 2 * 256) * 4;  // bias[2][256], head weights[256], head partials[3][128], LN column sums[2][256]
+constexpr int kLnRec = 32;                                      // floats per LayerNorm row record {c, P, (s1, s2) x P}
+constexpr int kLnBufBytes = 32 * 32;                            // staging buffer of the 16-bit centred copy: 32 rows x 16 columns
 #ifndef SPG_RES_SLOTS
 #define SPG_RES_SLOTS 3
 #endif
@@ -91,6 +93,13 @@ struct GemmArgs {
     const float* head_w;
     float head_b;
     float* head_out;
+    // LayerNorm folding (see spg_epilogue_t): consumer = fold_rec / fold_cw, producer = emit_rec / prev_rec (+ tmap_ln)
+    const float* ln_fold_rec;
+    const float* ln_fold_cw;
+    float* ln_emit_rec;
+    const float* ln_prev_rec;
+    float ln_inv_cols, ln_eps;
+    int ln_mode;      // 0 none, 1 consumer (fold), 2 producer (emit): selects the kernel instance
 };
 
 #ifdef SPG_TRACE
@@ -133,11 +142,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // M=256 MMAs that read both CTAs' smem and fill both CTAs' TMEM, every CTA runs the epilogue of its 128 rows.
 // Staging half of W per CTA shrinks the stage (28 KB instead of 40 KB at N=192): more stages in flight per
 // TMA round trip and 30 % less L2->smem traffic per FLOP.
-template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut, int kPair, int kEpiWarps, int kUp2 = 0>
+template <int kAct, int kOutF32, int kHasRes, int kHasHead, int kHasOut, int kPair, int kEpiWarps, int kUp2 = 0, int kLn = 0>
 __global__ void __launch_bounds__(64 + 32 * kEpiWarps, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                    const GemmArgs p) {
+                    const __grid_constant__ CUtensorMap tmap_ln, const GemmArgs p) {
     const int act = kAct < 0 ? p.act : kAct;
     const bool out_f32 = kOutF32 < 0 ? p.out_f32 != 0 : kOutF32 != 0;
     const bool has_res = kHasRes < 0 ? p.has_res != 0 : kHasRes != 0;
@@ -175,6 +184,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tma_prefetch_desc(&tmap_b);
         if (has_out) tma_prefetch_desc(&tmap_out);
         if (has_res) tma_prefetch_desc(&tmap_res);
+        if (kLn == 2) tma_prefetch_desc(&tmap_ln);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -382,7 +392,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float* bias_s = reinterpret_cast<float*>(smem_raw + (scratch_addr - raw_addr));
         float* headw_s = bias_s + 2 * 256;
         float* headp_s = headw_s + 256;
+        float* cw_s = headp_s + 3 * 128;  // [2][256] column sums of W' (kLn == 1)
         const uint32_t my_staging = staging_addr + ewarp * kResSlots * p.buf_bytes;
+        // kLn == 2: ring of 1 KB buffers for the 16-bit centred copy, slot-locked to the main ring
+        const uint32_t my_ln_staging = staging_addr + kEpiWarps * kResSlots * p.buf_bytes + ewarp * kResSlots * kLnBufBytes;
+        uint8_t* my_ln_staging_ptr = smem_raw + (my_ln_staging - raw_addr);
         uint8_t* my_staging_ptr = smem_raw + (my_staging - raw_addr);
         // Staging buffer = 32 rows x (group x 16) columns of the output type, rows of 32 / 64 / 128 bytes in
         // the matching TMA swizzle (32B / 64B / 128B): 16-byte piece j of row r sits at j ^ ((r >> shift) & mask),
@@ -437,6 +451,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
             float* bs = bias_s + buf * 256;
             if (etid < p.block_n) bs[etid] = (p.bias != nullptr && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
+            float* cws = cw_s + buf * 256;
+            if (kLn == 1 && etid < p.block_n) cws[etid] = n0 + etid < p.N ? __ldg(p.ln_fold_cw + n0 + etid) : 0.f;
+            // LayerNorm folding: this thread's row statistics (consumer) or centre (producer), from the row records
+            const int ln_row = row0 + lane;
+            float ln_rs = 1.f, ln_rm = 0.f, ln_c = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;
+            if (kLn == 1 && ln_row < p.M) {
+                const float* rec = p.ln_fold_rec + static_cast<size_t>(ln_row) * kLnRec;
+                const int parts = static_cast<int>(__ldg(rec + 1));
+                float s1 = 0.f, s2 = 0.f;
+                for (int i = 0; i < parts; ++i) {
+                    const float2 pr = __ldg(reinterpret_cast<const float2*>(rec + 2) + i);
+                    s1 += pr.x;
+                    s2 += pr.y;
+                }
+                const float m = s1 * p.ln_inv_cols;
+                const float var = fmaxf(s2 * p.ln_inv_cols - m * m, 0.f);
+                ln_rs = rsqrtf(var + p.ln_eps);
+                ln_rm = ln_rs * m;
+            }
+            if (kLn == 2 && p.ln_prev_rec != nullptr && ln_row < p.M) {
+                const float* rec = p.ln_prev_rec + static_cast<size_t>(ln_row % (p.res_rows > 0 ? p.res_rows : p.M)) * kLnRec;
+                const int parts = static_cast<int>(__ldg(rec + 1));
+                float s1 = 0.f;
+                for (int i = 0; i < parts; ++i) s1 += __ldg(rec + 2 + 2 * i);
+                ln_c = __ldg(rec) + s1 * p.ln_inv_cols;  // mean of the residual input row
+            }
 
             auto issue_res_load = [&](int sl, int c) {  // lane 0 only; c = first chunk of the group
                 const uint32_t bar = res_bar(ewarp, sl);
@@ -484,6 +524,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 b = b4[i];
+                    if (kLn == 1) {  // rstd * (acc - m * colsum(W')) + (b + W beta)
+                        const float4 cw = reinterpret_cast<const float4*>(cws + col)[i];
+                        v[4 * i + 0] = fmaf(__uint_as_float(raw[4 * i + 0]), ln_rs, fmaf(-ln_rm, cw.x, b.x));
+                        v[4 * i + 1] = fmaf(__uint_as_float(raw[4 * i + 1]), ln_rs, fmaf(-ln_rm, cw.y, b.y));
+                        v[4 * i + 2] = fmaf(__uint_as_float(raw[4 * i + 2]), ln_rs, fmaf(-ln_rm, cw.z, b.z));
+                        v[4 * i + 3] = fmaf(__uint_as_float(raw[4 * i + 3]), ln_rs, fmaf(-ln_rm, cw.w, b.w));
+                        continue;
+                    }
                     v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x;
                     v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
                     v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
@@ -516,6 +564,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         v[4 * i + 2] += r.z;
                         v[4 * i + 3] += r.w;
                     }
+                }
+                if (kLn == 2) {  // centred 16-bit copy for the consumer GEMMs + this thread's partial row statistics
+                    float vc[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        vc[i] = v[i] - ln_c;
+                        ln_s1 += vc[i];
+                        ln_s2 = fmaf(vc[i], vc[i], ln_s2);
+                    }
+                    uint8_t* lst = my_ln_staging_ptr + slot * kLnBufBytes + lane * 32;
+                    const uint32_t lx = (lane >> 2) & 1u;  // 32-byte swizzle: the two 16-byte pieces swap on rows 4..7 of 8
+                    *reinterpret_cast<uint4*>(lst + ((0u ^ lx) << 4)) =
+                        make_uint4(pack2(vc[0], vc[1]), pack2(vc[2], vc[3]), pack2(vc[4], vc[5]), pack2(vc[6], vc[7]));
+                    *reinterpret_cast<uint4*>(lst + ((1u ^ lx) << 4)) =
+                        make_uint4(pack2(vc[8], vc[9]), pack2(vc[10], vc[11]), pack2(vc[12], vc[13]), pack2(vc[14], vc[15]));
                 }
                 if (has_head) {
                     const float4* w4 = reinterpret_cast<const float4*>(headw_s + col);
@@ -555,6 +618,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             } else {
                                 tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, row0);
                             }
+                            if (kLn == 2) tma_store_2d(&tmap_ln, my_ln_staging + slot * kLnBufBytes, n0 + c_first * 16, row0);
                             tma_store_commit();
                         }
                     }
@@ -578,6 +642,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (c + 2 < c_end) tmem_ld16(taddr + (c + 2) * 16, ra);
                     process(rb, c + 1, !pair, true);
                 }
+            }
+            if (kLn == 2 && ln_row < p.M) {  // row record: fixed slot per (n-tile, column slice) -> deterministic statistics
+                float* rec = p.ln_emit_rec + static_cast<size_t>(ln_row) * kLnRec;
+                reinterpret_cast<float2*>(rec + 2)[n_blk * kParts + part] = make_float2(ln_s1, ln_s2);
+                if (n_blk == 0 && part == 0) *reinterpret_cast<float2*>(rec) = make_float2(ln_c, static_cast<float>(p.num_n_tiles * kParts));
             }
             // accumulator fully read: hand the TMEM stage back to the MMA warp
             if (ewarp == 0 && lane == 0) SPG_STAMP(trace_i, 9);
@@ -617,7 +686,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // Tile width.  256-wide tiles run the tensor pipe ~15 % faster than 192-wide ones (measured 1347 vs 1150 TFLOP/s at
 // long K), so when N is not a multiple of 256 but the padding of a ragged last tile costs <= 12 % (N = 1728, 3456,
 // 1152: 3.7 / 3.7 / 11 %) the launch uses 256-wide tiles with a ragged tail; otherwise the largest divisor of N.
-int pick_block_n(int N, int num_m_tiles = 1 << 20) {
+// max_n_tiles bounds the number of n-tiles (fused head: 1; LayerNorm producer: 7 = the partial slots of a row record)
+int pick_block_n(int N, int num_m_tiles = 1 << 20, int max_n_tiles = 1 << 20) {
     static const int ragged_env = [] { const char* e = getenv("SPG_GEMM_RAGGED"); return e ? atoi(e) : 1; }();
     static const int small_env0 = [] { const char* e = getenv("SPG_GEMM_SMALLM"); return e ? atoi(e) : 1; }();
     const bool small = small_env0 && num_m_tiles * ((N + 255) / 256) * 2 <= sm_count();
@@ -638,7 +708,7 @@ int pick_block_n(int N, int num_m_tiles = 1 << 20) {
     static const int small_env = [] { const char* e = getenv("SPG_GEMM_SMALLM"); return e ? atoi(e) : 1; }();
     if (small_env && best > 64 && num_m_tiles * ((N + best - 1) / best) * 2 <= sm_count()) {
         for (int bn = 64; bn < best; bn += 16)
-            if (N % bn == 0 && num_m_tiles * (N / bn) <= sm_count()) return bn;
+            if (N % bn == 0 && num_m_tiles * (N / bn) <= sm_count() && N / bn <= max_n_tiles) return bn;
     }
     return best;
 }
@@ -659,7 +729,7 @@ void decide_pair(GemmArgs& a) {
 }
 
 struct EpiMaps {
-    CUtensorMap out, res;
+    CUtensorMap out, res, ln;
 };
 
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, cudaStream_t stream) {
@@ -668,7 +738,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     a.reverse = traversal_reversed() ? 1 : 0;
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
     const int stage_bytes = a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128;
-    const int staging = a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0;
+    const int staging = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
+                        (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0);
     const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -708,7 +779,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
             SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
             attr_set = true;                                                                                       \
         }                                                                                                          \
-        SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, a));                                 \
+        SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, em.ln, a));                                 \
     } while (0)
 #define SPG_LAUNCH_ONE_UP2(PAIR)                                                                                   \
     do {                                                                                                           \
@@ -718,7 +789,22 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
             SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
             attr_set = true;                                                                                       \
         }                                                                                                          \
-        SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, a));                                 \
+        SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, em.ln, a));                                 \
+    } while (0)
+#define SPG_LAUNCH_ONE_LN(ACT, F32, RES, PAIR, LN)                                                                 \
+    do {                                                                                                           \
+        auto kern = gemm_tcgen05_kernel<ACT, F32, RES, 0, 1, PAIR, kEpiWarpsDefault, 0, LN>;                        \
+        static bool attr_set = false;                                                                              \
+        if (!attr_set) {                                                                                           \
+            SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
+            attr_set = true;                                                                                       \
+        }                                                                                                          \
+        SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, em.ln, a));                          \
+    } while (0)
+#define SPG_LAUNCH_LN(ACT, F32, RES, LN)                       \
+    do {                                                       \
+        if (pair) SPG_LAUNCH_ONE_LN(ACT, F32, RES, 1, LN);     \
+        else SPG_LAUNCH_ONE_LN(ACT, F32, RES, 0, LN);          \
     } while (0)
 #define SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, EW)                     \
     do {                                                             \
@@ -726,7 +812,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
         else SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, 0, EW);        \
     } while (0)
 #define SPG_LAUNCH_EW(ACT, F32, RES, HEAD, OUT) SPG_LAUNCH(ACT, F32, RES, HEAD, OUT, kEpiWarpsDefault)
-    if (a.up2) {
+    if (a.ln_mode == 1) {  // LayerNorm consumer: qkv (no act), fc1 (GELU), dim-change proj (fp32 out)
+        if (a.act == SPG_ACT_GELU) SPG_LAUNCH_LN(SPG_ACT_GELU, 0, 0, 1);
+        else if (a.out_f32) SPG_LAUNCH_LN(SPG_ACT_NONE, 1, 0, 1);
+        else SPG_LAUNCH_LN(SPG_ACT_NONE, 0, 0, 1);
+    } else if (a.ln_mode == 2) {  // LayerNorm producer: fp32 residual GEMM that also emits the centred copy + records
+        SPG_LAUNCH_LN(SPG_ACT_NONE, 1, 1, 2);
+    } else if (a.up2) {
         if (pair) SPG_LAUNCH_ONE_UP2(1);
         else SPG_LAUNCH_ONE_UP2(0);
     } else if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_NONE, 0, 0, 0, 1);
@@ -738,6 +830,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     else if (a.act == SPG_ACT_RELU && !a.has_res && head && !a.has_out) SPG_LAUNCH_EW(SPG_ACT_RELU, 0, 0, 1, 0);
     else SPG_LAUNCH(-1, -1, -1, -1, -1, kEpiWarpsDefault);
 #undef SPG_LAUNCH_EW
+#undef SPG_LAUNCH_LN
+#undef SPG_LAUNCH_ONE_LN
 #undef SPG_LAUNCH_ONE_UP2
 #undef SPG_LAUNCH
 #undef SPG_LAUNCH_ONE
@@ -780,11 +874,40 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
     a.head_w = ep->head_w;
     a.head_b = ep->head_b;
     a.head_out = ep->head_w != nullptr ? ep->head_out : nullptr;
+    // LayerNorm folding
+    a.ln_mode = 0;
+    if (ep->ln_fold_rec != nullptr) {
+        SPG_CHECK_ARG(ep->ln_fold_cw != nullptr && ep->ln_cols > 0, "ln_fold_rec needs ln_fold_cw and ln_cols");
+        SPG_CHECK_ARG(ep->head_w == nullptr && ep->residual == nullptr && ep->out != nullptr && ep->act != SPG_ACT_RELU &&
+                      !(ep->act == SPG_ACT_GELU && ep->out_dtype == SPG_F32),
+                      "LayerNorm folding is built for: no act / GELU with 16-bit out, no act with fp32 out; no residual, no head");
+        SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->ln_fold_rec) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_fold_cw) & 15) == 0,
+                      "ln_fold_rec / ln_fold_cw must be 16-byte aligned");
+        a.ln_mode = 1;
+        a.ln_fold_rec = ep->ln_fold_rec;
+        a.ln_fold_cw = ep->ln_fold_cw;
+    }
+    if (ep->ln_emit_out != nullptr) {
+        SPG_CHECK_ARG(a.ln_mode == 0, "a GEMM cannot both consume and produce a folded LayerNorm");
+        SPG_CHECK_ARG(ep->ln_emit_rec != nullptr && ep->ln_cols == N, "ln_emit_out needs ln_emit_rec and ln_cols == N");
+        SPG_CHECK_ARG(ep->residual != nullptr && ep->out_dtype == SPG_F32 && ep->act == SPG_ACT_NONE && ep->head_w == nullptr,
+                      "the LayerNorm producer is the fp32 residual GEMM (no activation, no head)");
+        SPG_CHECK_ARG(a.num_n_tiles * 2 <= (kLnRec - 2) / 2, "too many n-tiles (%d) for a LayerNorm row record", a.num_n_tiles);
+        SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->ln_emit_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_emit_rec) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(ep->ln_prev_rec) & 15) == 0, "LayerNorm buffers must be 16-byte aligned");
+        a.ln_mode = 2;
+        a.ln_emit_rec = ep->ln_emit_rec;
+        a.ln_prev_rec = ep->ln_prev_rec;
+    }
+    a.ln_inv_cols = ep->ln_cols > 0 ? 1.0f / static_cast<float>(ep->ln_cols) : 0.f;
+    a.ln_eps = ep->ln_eps;
     memset(&em, 0, sizeof(em));
     if (a.has_out)
         if (int rc = make_tmap_epilogue(&em.out, ep->out, M, N, a.out_f32, a.group * 16)) return rc;
     if (a.has_res)
         if (int rc = make_tmap_epilogue(&em.res, ep->residual, ep->res_rows > 0 ? ep->res_rows : M, N, 1, a.group * 16)) return rc;
+    if (a.ln_mode == 2)
+        if (int rc = make_tmap_epilogue(&em.ln, ep->ln_emit_out, M, N, 0, 16)) return rc;
     return SPG_OK;
 }
 
@@ -803,7 +926,7 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.M = M;
     a.N = N;
     a.num_m_tiles = (M + kBlockM - 1) / kBlockM;
-    a.block_n = pick_block_n(N, a.num_m_tiles);
+    a.block_n = pick_block_n(N, a.num_m_tiles, ep != nullptr && ep->head_w != nullptr ? 1 : (ep != nullptr && ep->ln_emit_out != nullptr ? 7 : 1 << 20));
     a.num_n_tiles = (N + a.block_n - 1) / a.block_n;
     a.num_k_chunks = (K + kBlockK - 1) / kBlockK;
     a.conv = 0;

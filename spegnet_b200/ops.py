@@ -43,7 +43,7 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optiona
     return t.data_ptr()
 
 
-def _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out) -> Epilogue:
+def _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_fold=None, ln_emit=None) -> Epilogue:
     ep = Epilogue()
     ep.bias = _ptr(bias, torch.float32, "bias")
     ep.act = act
@@ -57,17 +57,30 @@ def _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out) -> E
     ep.head_w = _ptr(head_w, torch.float32, "head_w")
     ep.head_b = float(head_b)
     ep.head_out = _ptr(head_out, torch.float32, "head_out")
+    if ln_fold is not None:  # (records [M,32] fp32, colsum(W') [N] fp32, channels, eps): see spg_epilogue_t
+        rec, cw, cols, eps = ln_fold
+        ep.ln_fold_rec = _ptr(rec, torch.float32, "ln_fold_rec")
+        ep.ln_fold_cw = _ptr(cw, torch.float32, "ln_fold_cw")
+        ep.ln_cols, ep.ln_eps = int(cols), float(eps)
+    if ln_emit is not None:  # (records out [M,32] fp32, previous records or None, centred 16-bit copy [M,N])
+        rec, prev, xc = ln_emit
+        ep.ln_emit_rec = _ptr(rec, torch.float32, "ln_emit_rec")
+        ep.ln_prev_rec = _ptr(prev, torch.float32, "ln_prev_rec")
+        ep.ln_emit_out = _ptr(xc, H16, "ln_emit_out")
+        ep.ln_cols = int(xc.shape[1])
     return ep
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bias=None, act=ACT_NONE,
-           residual=None, res_rows: int = 0, head_w=None, head_b: float = 0.0, head_out=None) -> None:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; see spg_linear_h16."""
+           residual=None, res_rows: int = 0, head_w=None, head_b: float = 0.0, head_out=None, ln_fold=None,
+           ln_emit=None) -> None:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; see spg_linear_h16.  `ln_fold` / `ln_emit` fold the
+    LayerNorm between a residual GEMM (producer) and the GEMMs reading its output (consumers), see spg_epilogue_t."""
     M, K = a.shape
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f"weight K {w.shape[1]} != activation K {K}")
-    ep = _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out)
+    ep = _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_fold, ln_emit)
     lib, dn = _lib_for(a)
     _lib.flip_direction()
     rc = lib.spg_linear_h16(_ptr(a, H16, "a"), _ptr(w, H16, "w"), M, N, K,

@@ -313,3 +313,55 @@ def test_conv3x3_up2_matches_interpolate_then_conv(ops, B, H, W, Cin, Cout):
         assert torch.isfinite(sl.float()).all()
     _close(out[:, :, :2], ref[:, :, :2], 2e-2, 1e-2)
     _close(out[:, :, -2:], ref[:, :, -2:], 2e-2, 1e-2)
+
+
+@pytest.mark.parametrize("M,C,N2", [(1024, 576, 1728), (4096, 144, 576), (300, 288, 864), (65536, 576, 2304)])
+def test_layernorm_folded_into_producer_and_consumer(ops, M, C, N2):
+    """LayerNorm folded into the GEMMs around it: a residual GEMM (producer) emits the centred 16-bit copy + row
+    records, a second GEMM (consumer) applies rstd / mean in its epilogue.  Reference: the unfused chain
+    x = res + a W1^T + b1;  y = LayerNorm(x) * gamma + beta;  out = gelu(y W2^T + b2)  in fp32."""
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    K1 = 128
+    a = _bf(torch.randn(M, K1, device="cuda", generator=g))
+    w1 = _bf(torch.randn(C, K1, device="cuda", generator=g) / math.sqrt(K1))
+    b1 = torch.randn(C, device="cuda", generator=g)
+    # residual rows with a large common offset: the centring by the previous mean must absorb it
+    res = torch.randn(M, C, device="cuda", generator=g) + 6.0 * torch.randn(M, 1, device="cuda", generator=g)
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g) * 0.3
+    w2 = torch.randn(N2, C, device="cuda", generator=g) / math.sqrt(C)
+    b2 = torch.randn(N2, device="cuda", generator=g)
+    # records of the residual input rows, as an earlier producer would have left them: {c = 0, P = 1, (sum, sum sq)}
+    prev = torch.zeros(M, 32, device="cuda")
+    prev[:, 1] = 1.0
+    prev[:, 2] = res.sum(1)
+    prev[:, 3] = (res * res).sum(1)
+    x = torch.empty(M, C, device="cuda")
+    x.copy_(res)
+    xc = torch.empty(M, C, device="cuda", dtype=H16)
+    rec = torch.full((M, 32), float("nan"), device="cuda")
+    ops.linear(a, w1, x, bias=b1, residual=x, ln_emit=(rec, prev, xc))
+    x_ref = res + a.float() @ w1.float().t() + b1
+    _close(x, x_ref, 2e-2, 1e-2)
+    centre = res.mean(1, keepdim=True)
+    _close(xc, x_ref - centre, 2e-2, 1e-2)
+    assert torch.allclose(rec[:, 0], centre[:, 0], atol=1e-4)
+    parts = rec[:, 1].long()
+    assert int(parts.min()) == int(parts.max()) and 2 <= int(parts[0]) <= 15
+    P = int(parts[0])
+    s1 = rec[:, 2:2 + 2 * P:2].sum(1)
+    s2 = rec[:, 3:3 + 2 * P:2].sum(1)
+    d = x_ref - centre
+    assert torch.allclose(s1, d.sum(1), atol=2e-2, rtol=1e-3) and torch.allclose(s2, (d * d).sum(1), atol=5e-2, rtol=2e-3)
+    # consumer: W' = W diag(gamma) (16-bit), colsum(W') of the ROUNDED W', bias' = b + W beta
+    w2p = _bf(w2 * gamma[None, :]).contiguous()
+    cw = w2p.float().sum(1).contiguous()
+    b2p = (b2 + w2 @ beta).contiguous()
+    for act, out_dtype in ((ops.ACT_GELU, H16), (ops.ACT_NONE, H16), (ops.ACT_NONE, torch.float32)):
+        out = torch.empty(M, N2, device="cuda", dtype=out_dtype)
+        ops.linear(xc, w2p, out, bias=b2p, act=act, ln_fold=(rec, cw, C, 1e-6))
+        y = F.layer_norm(x_ref, (C,), gamma, beta, 1e-6)
+        ref = y @ w2.t() + b2
+        if act == ops.ACT_GELU:
+            ref = F.gelu(ref)
+        _close(out, ref, 3e-2, 1.5e-2)
