@@ -168,6 +168,8 @@ class _Workspace:
         self.bord = e(2 * B * 4 * h * 9 * 128, bf).view(2, B * 4 * h, 9 * 128)
         self.corr = e(2 * B * 4 * h * 256, f32).view(2, B * 4 * h, 256)
         self.d3a = e(B * 64 * h * h * 64, bf).view(B, 8 * h, 8 * h, 64)
+        # LayerNorm row records {c, P, (sum, sum sq) x P} of the residual stream, ping-pong (see spg_epilogue_t)
+        self.rec = [e(T[0] * 32, f32).view(T[0], 32) for _ in range(2)]
         self.pos: Optional[torch.Tensor] = None  # [G*G, 144] fp32, set by the model (input independent)
 
 
@@ -208,6 +210,11 @@ class SPEGNet(nn.Module):
             _attach(self, full, _default_init(full, shape), "param")
         for name, (shape, kind) in head_entries(tuple(self.in_channels_list)).items():
             _attach(self, name, _default_init(name, shape), "param" if kind == "param" else "buffer")
+        # LayerNorm folded into the GEMMs around it (`_trunk_ln_folded`): removes the 96 LayerNorm launches and 10 GB of
+        # traffic per batch-64 step, but measured 972 vs 981 img/s at batch 64 (the residual GEMMs pay for the second
+        # store and the consumers for reading the row records) and 3.00 vs 3.09 ms at batch 1, and the row statistics
+        # then depend on the n-tiling, i.e. on the batch size, in the last bit.  Off by default (SPG_LN_FUSE=1 enables).
+        self.ln_fuse = os.environ.get("SPG_LN_FUSE", "0") != "0"
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._debug_taps: Optional[Dict[str, torch.Tensor]] = None  # tests: stream snapshot after every block
         self._workspaces: Dict[Tuple[int, int, str], _Workspace] = {}
@@ -262,6 +269,15 @@ class SPEGNet(nn.Module):
                 if src + a + ".weight" in sd:
                     W[dst + c + ".w"] = f32(sd[src + a + ".weight"]).to(bf).contiguous()
                     W[dst + c + ".b"] = f32(sd[src + a + ".bias"])
+            # LayerNorm folded into its consumers: W' = W diag(gamma) (16 bit), column sums of the ROUNDED W' (they
+            # multiply the row mean that the 16-bit operand still carries), bias' = b + W beta in fp32
+            for c, n in (("qkv", "n1"), ("proj", "n1"), ("fc1", "n2")):
+                if dst + c + ".w" in W:
+                    wf = f32(sd[src + {"qkv": "attn.qkv", "proj": "proj", "fc1": "mlp.layers.0"}[c] + ".weight"])
+                    wl = (wf * W[dst + n + ".w"][None, :]).to(bf).contiguous()
+                    W[dst + c + ".wl"] = wl
+                    W[dst + c + ".cw"] = wl.float().sum(dim=1).contiguous()
+                    W[dst + c + ".bl"] = (W[dst + c + ".b"] + wf @ W[dst + n + ".b"]).contiguous()
 
         def bn_fold(prefix: str):
             g, be = f32(sd[prefix + "weight"]), f32(sd[prefix + "bias"])
@@ -409,6 +425,8 @@ class SPEGNet(nn.Module):
                 "features": LazyFeatures({k: v.clone() for k, v in raw.items()})}
 
     def _trunk(self, W, ws: _Workspace, x: torch.Tensor, B: int, S: int) -> None:
+        if self.ln_fuse and self._debug_taps is None:
+            return self._trunk_ln_folded(W, ws, x, B, S)
         G = S // 4
         ops.patchify(x, ws.cols)
         ops.linear(ws.cols, W["pe.w"], ws.x[0], bias=W["pe.b"], residual=ws.pos, res_rows=G * G)
@@ -446,6 +464,56 @@ class SPEGNet(nn.Module):
             cur, H = nxt, Ho
             if self._debug_taps is not None:
                 self._debug_taps[f"block{b.index}"] = cur.view(B, H, H, b.dim_out).clone()
+            if b.index in ends and b.stage >= 1:
+                ops.cast_h16(cur, ws.f[b.stage])
+
+    def _trunk_ln_folded(self, W, ws: _Workspace, x: torch.Tensor, B: int, S: int) -> None:
+        """The trunk with every LayerNorm folded into the GEMMs around it (no LayerNorm launches): each residual GEMM
+        (patch embed + pos, attention proj, fc2) also emits the centred 16-bit copy of its output rows and their
+        statistics; qkv / fc1 / the dim-change proj consume them (spg_epilogue_t, `ln_*` fields)."""
+        G = S // 4
+        ends = self.spec.stage_ends
+        rec_cur, rec_oth = ws.rec
+        ops.patchify(x, ws.cols)
+        H = G
+        cur = ws.x[0]
+        xh = ws.y[: B * G * G * self.spec.embed_dim].view(B * G * G, self.spec.embed_dim)
+        ops.linear(ws.cols, W["pe.w"], cur, bias=W["pe.b"], residual=ws.pos, res_rows=G * G,
+                   ln_emit=(rec_cur[: B * G * G], None, xh))
+        last = self.blocks[-1].index
+        for b in self.blocks:
+            p = f"b{b.index}."
+            M = B * H * H
+            r1 = rec_cur[:M]
+            if b.dim_in != b.dim_out:
+                if not b.q_pool:
+                    raise NotImplementedError("channel change without query pooling does not occur in Hiera-L")
+                Ho = H // 2
+                Mo = B * Ho * Ho
+                nxt = ws.x[b.stage]
+                proj = ws.proj[: M * b.dim_out].view(M, b.dim_out)
+                ops.linear(xh, W[p + "proj.wl"], proj, bias=W[p + "proj.bl"], ln_fold=(r1, W[p + "proj.cw"], b.dim_in, LN_EPS))
+                ops.maxpool2x2(proj, nxt, B, H, H, b.dim_out)  # pooled shortcut lands in the new stream
+                prev = None                                    # new stream: no earlier statistics of these rows
+            else:
+                Ho, Mo, nxt = H, M, cur
+                prev = r1
+            qkv = ws.qkv[: M * 3 * b.dim_out].view(M, 3 * b.dim_out)
+            ops.linear(xh, W[p + "qkv.wl"], qkv, bias=W[p + "qkv.bl"], ln_fold=(r1, W[p + "qkv.cw"], b.dim_in, LN_EPS))
+            att = ws.att[: Mo * b.dim_out].view(Mo, b.dim_out)
+            ops.window_attention(qkv, att, B, H, H, b.dim_out, b.heads, b.window, b.q_pool)
+            z = ws.y[: Mo * b.dim_out].view(Mo, b.dim_out)
+            r2 = rec_oth[:Mo]
+            ops.linear(att, W[p + "ap.w"], nxt, bias=W[p + "ap.b"], residual=nxt, ln_emit=(r2, prev, z))
+            hid = ws.hid[: Mo * 4 * b.dim_out].view(Mo, 4 * b.dim_out)
+            ops.linear(z, W[p + "fc1.wl"], hid, bias=W[p + "fc1.bl"], act=ops.ACT_GELU,
+                       ln_fold=(r2, W[p + "fc1.cw"], b.dim_out, LN_EPS))
+            if b.index != last:  # the next block's LayerNorm reads this output
+                xh = ws.y[: Mo * b.dim_out].view(Mo, b.dim_out)
+                ops.linear(hid, W[p + "fc2.w"], nxt, bias=W[p + "fc2.b"], residual=nxt, ln_emit=(rec_cur[:Mo], r2, xh))
+            else:
+                ops.linear(hid, W[p + "fc2.w"], nxt, bias=W[p + "fc2.b"], residual=nxt)
+            cur, H = nxt, Ho
             if b.index in ends and b.stage >= 1:
                 ops.cast_h16(cur, ws.f[b.stage])
 

@@ -226,3 +226,21 @@ def test_host_pipeline_returns_the_forward_results_in_order(spread_sd):
     assert len(got) == len(want)
     for (gp, ge), (wp, we) in zip(got, want):
         assert torch.equal(gp, wp) and torch.equal(ge, we)
+
+
+def test_layernorm_folded_trunk_keeps_mask_parity(spread_sd):
+    """The opt-in trunk with every LayerNorm folded into its producer / consumer GEMMs (model.ln_fuse) against the
+    fp32 oracle: same 1e-2 mask bar as the default path."""
+    from oracle.spegnet import spegnet_forward
+    from spegnet_b200 import SPEGNet
+
+    model = SPEGNet({"encoder": {"config_path": "", "checkpoint_path": "", "variant": "large"}})
+    model.load_state_dict(spread_sd)
+    model.ln_fuse = True
+    model = model.cuda().eval()
+    x = _images(2, 256, seed=9)
+    with torch.no_grad():
+        got = model(x.cuda())
+    ref = spegnet_forward(spread_sd, x)
+    for g, w in zip(got["predictions"] + [got["edge"]], ref["predictions"] + [ref["edge"]]):
+        assert float((g.cpu().sigmoid() - w.sigmoid()).abs().max()) <= 1e-2
