@@ -272,7 +272,7 @@ def main():
 
     torch.manual_seed(0)  # identical random-init weights on every rank
     model = SPEGNet(CFG, compute_dtype=torch.float16 if args.dtype == "fp16" else torch.bfloat16)
-    cpu_sd = {k: v.clone() for k, v in model.state_dict().items()} if (rank == 0 and not args.no_cpu_baseline) else None
+    cpu_sd = {k: v.clone() for k, v in model.state_dict().items()} if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     model = model.to(dev).eval()
 
     B, S = args.batch, args.size
