@@ -135,7 +135,7 @@ class LazyFeatures(Mapping):
 class _Workspace:
     """Device buffers for one (batch, resolution); reused across forwards on the same stream."""
 
-    def __init__(self, B: int, S: int, dev: torch.device, spec: TrunkSpec, h16: torch.dtype):
+    def __init__(self, B: int, S: int, dev: torch.device, spec: TrunkSpec, h16: torch.dtype, ln_records: bool = False):
         bf, f32 = h16, torch.float32
         d = spec.dims
         G = S // 4
@@ -169,7 +169,7 @@ class _Workspace:
         self.corr = e(2 * B * 4 * h * 256, f32).view(2, B * 4 * h, 256)
         self.d3a = e(B * 64 * h * h * 64, bf).view(B, 8 * h, 8 * h, 64)
         # LayerNorm row records {c, P, (sum, sum sq) x P} of the residual stream, ping-pong (see spg_epilogue_t)
-        self.rec = [e(T[0] * 32, f32).view(T[0], 32) for _ in range(2)]
+        self.rec = [e(T[0] * 32, f32).view(T[0], 32) for _ in range(2)] if ln_records else None
         self.pos: Optional[torch.Tensor] = None  # [G*G, 144] fp32, set by the model (input independent)
 
 
@@ -379,7 +379,7 @@ class SPEGNet(nn.Module):
         return self._forward_eager(x, B, S)
 
     def _new_workspace(self, x: torch.Tensor, B: int, S: int) -> _Workspace:
-        ws = _Workspace(B, S, x.device, self.spec, self.compute_dtype)
+        ws = _Workspace(B, S, x.device, self.spec, self.compute_dtype, ln_records=self.ln_fuse)
         ws.pos = self._pos_map(self._packed, S // 4)
         return ws
 
@@ -425,7 +425,7 @@ class SPEGNet(nn.Module):
                 "features": LazyFeatures({k: v.clone() for k, v in raw.items()})}
 
     def _trunk(self, W, ws: _Workspace, x: torch.Tensor, B: int, S: int) -> None:
-        if self.ln_fuse and self._debug_taps is None:
+        if self.ln_fuse and self._debug_taps is None and ws.rec is not None:
             return self._trunk_ln_folded(W, ws, x, B, S)
         G = S // 4
         ops.patchify(x, ws.cols)
