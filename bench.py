@@ -180,7 +180,7 @@ def run_dataset(args):
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+        _init_nccl(dist, dev)
     torch.manual_seed(0)
     model = SPEGNet(CFG, compute_dtype=torch.float16 if args.dtype == "fp16" else torch.bfloat16).to(dev).eval()
     N, B, S = args.dataset, args.batch, args.size
@@ -228,6 +228,29 @@ def run_dataset(args):
         dist.destroy_process_group()
 
 
+class _StdoutToStderr:
+    """File-descriptor level redirect: NCCL prints its version banner straight to fd 1 while the communicator is
+    created, and stdout has to carry exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
+def _init_nccl(dist, dev):
+    with _StdoutToStderr():
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()  # creates the communicator (and its banner) now, not inside the timed region
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -265,7 +288,7 @@ def main():
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+        _init_nccl(dist, dev)
     lib = _lib.load(args.dtype)
     if lib.spg_device_check() != 0:
         raise SystemExit(lib.spg_last_error().decode())
