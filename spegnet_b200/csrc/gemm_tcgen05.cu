@@ -63,6 +63,7 @@ struct GemmArgs {
     int M, N;
     int block_n;
     int num_m_tiles, num_n_tiles, num_k_chunks;
+    int last_chunk_ksteps;  // 16-deep MMA steps that hold real data in the LAST 64-wide k-chunk (K tail; 4 when K % 64 == 0)
     int stages;
     int reverse;     // walk the tiles in descending order (see common.h "Traversal direction")
     int l2_prefetch; // linear mode: prefetch the next tile's A rows into L2 one tile ahead
@@ -358,8 +359,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     } else {
                         const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
                         const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kAStageBytes);
+                        // K tail (K = 144 / 288 / 168 in stages 1-2 and the patch embedding): the zero-filled k-steps of
+                        // the last chunk are not issued at all (25 % / 10 % of those GEMMs' tensor work)
+                        const int ksteps = kc == p.num_k_chunks - 1 ? p.last_chunk_ksteps : kBlockK / kUmmaK;
 #pragma unroll
                         for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            if (k >= ksteps) break;
                             // advance 32 B (= 16 elements) along K inside the 128 B swizzle atom
                             const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
                             mma(d_tmem, a_desc + koff, b_desc + koff, (kc | k) != 0);
@@ -929,6 +934,7 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.block_n = pick_block_n(N, a.num_m_tiles, ep != nullptr && ep->head_w != nullptr ? 1 : (ep != nullptr && ep->ln_emit_out != nullptr ? 7 : 1 << 20));
     a.num_n_tiles = (N + a.block_n - 1) / a.block_n;
     a.num_k_chunks = (K + kBlockK - 1) / kBlockK;
+    a.last_chunk_ksteps = (K - (a.num_k_chunks - 1) * kBlockK + kUmmaK - 1) / kUmmaK;
     a.conv = 0;
     a.H = a.W = 1;
     a.cin_chunks = 1;
@@ -965,6 +971,7 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     a.num_n_tiles = Cout / a.block_n;
     a.cin_chunks = Cin / kBlockK;
     a.num_k_chunks = 9 * a.cin_chunks;
+    a.last_chunk_ksteps = kBlockK / kUmmaK;
     a.conv = 1;
     a.H = H;
     a.W = W;
@@ -1001,6 +1008,7 @@ extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const flo
     a.num_n_tiles = 1;
     a.cin_chunks = Cin / kBlockK;
     a.num_k_chunks = 9 * a.cin_chunks;
+    a.last_chunk_ksteps = kBlockK / kUmmaK;
     a.conv = 1;
     a.H = H;
     a.W = W;
