@@ -368,6 +368,9 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
         static const int tc_env = [] { const char* e = getenv("SPG_ATTN_TC"); return e ? atoi(e) : 1; }();
         if (tc_env && window == 16 && !q_pool && H % 16 == 0 && W % 16 == 0 && D == heads * 72)
             return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, stream);
+        // global blocks (window == 0) on a 32 / 64 / 128-wide token grid: two-pass tcgen05 kernel (SPG_ATTN_TC=2: windows only)
+        if (tc_env == 1 && window == 0 && !q_pool && H == W && (W == 32 || W == 64 || W == 128) && D == heads * 72)
+            return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, stream);
     }
     SPG_CHECK_ARG(heads > 0 && D == heads * kHd, "attention is specialised for head_dim 72 (D=%d heads=%d)", D, heads);
     int ws = window;

@@ -306,6 +306,335 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Global attention (window == 0: the three global blocks of stage 3, 1024 keys at 512^2 and 4096 at 1024^2) on
+// tcgen05 / TMEM.  A work item is (image, head, 256 consecutive queries) = two 128-query tiles, one TMEM region each;
+// the keys are streamed in blocks of 128 through two 3-stage TMA rings (K and V).  The softmax is exact and two-pass:
+//   pass A  for every key block: S = Q K_j^T (SS-MMA, N = 128) -> the row's warp group folds it into the running maximum;
+//   pass B  for every key block: S again -> p = 2^(s * scale - m) written back to TMEM as packed 16-bit pairs over the
+//           consumed S columns -> O += P V_j (TS-MMA, V MN-major) accumulating in TMEM across ALL key blocks.
+// Recomputing S costs 1.5x the MMA work of an online softmax but needs no rescaling of O in TMEM, and the tensor pipe
+// is the idle resource of this kernel (the exp2 on the MUFU and the TMEM round trips are the busy ones).  tcgen05.mma
+// instructions issued by one thread execute in order, so S_{j+1} may be issued right behind PV_j although it overwrites
+// the P_j columns.  Region layout (256 columns each): S / P in [0,128), O dims 0..63 in [128,192), dims 64..79 in
+// [192,208).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGKeys = 128;                    // keys per block
+constexpr int kGStages = 3;                    // K / V ring depth
+constexpr uint32_t kGTileMain = 128 * 128;     // 128 tokens x dims 0..63 (SWIZZLE_128B)
+constexpr uint32_t kGTileTail = 128 * 32;      // dims 64..79 (SWIZZLE_32B, 72..79 zero-filled)
+constexpr uint32_t kGTile = kGTileMain + kGTileTail;
+constexpr uint32_t kGOffQ = 0;                               // 2 query tiles: mains, then tails
+constexpr uint32_t kGOffK = 2 * kGTile;                      // kGStages x (main | tail)
+constexpr uint32_t kGOffV = kGOffK + kGStages * kGTile;
+constexpr uint32_t kGOffBar = kGOffV + kGStages * kGTile;    // 163840
+constexpr uint32_t kSmemG = kGOffBar + 512 + 1024;
+
+struct AttnGlobalParams {
+    h16* out;
+    int B, H, W, D, heads;
+    int rows_per_tile;  // grid rows per 128-token tile (128 / W)
+    int tiles_per_img;  // H*W / 128
+    int items;          // B * heads * tiles_per_img / 2
+    int nkb;            // key blocks per image (= tiles_per_img)
+    int reverse;
+    float scale_log2e;
+};
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_tail,
+                           const AttnGlobalParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar = base + kGOffBar;
+    const uint32_t q_full = bar, q_empty = bar + 8, k_full = bar + 16, k_empty = bar + 40, v_full = bar + 64,
+                   v_empty = bar + 88, s_full = bar + 112, sa_free = bar + 128, p_full = bar + 144, pv_done = bar + 160,
+                   o_read = bar + 176, tmem_slot = bar + 192;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_main);
+        tma_prefetch_desc(&tmap_tail);
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int s = 0; s < kGStages; ++s) {
+            mbar_init(k_full + 8 * s, 1);
+            mbar_init(k_empty + 8 * s, 1);
+            mbar_init(v_full + 8 * s, 1);
+            mbar_init(v_empty + 8 * s, 1);
+        }
+        for (int r = 0; r < 2; ++r) {
+            mbar_init(s_full + 8 * r, 1);
+            mbar_init(sa_free + 8 * r, 4);  // one arrive per warp of the region's warp group
+            mbar_init(p_full + 8 * r, 4);
+            mbar_init(pv_done + 8 * r, 1);
+            mbar_init(o_read + 8 * r, 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    pdl_launch_dependents();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_wait();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int pairs_per_img = p.tiles_per_img / 2;
+    // item -> (head, first grid row of the image, first query tile of the pair)
+    auto decode = [&](int item, int& head, int& img_row0, int& qtile0) {
+        if (p.reverse) item = p.items - 1 - item;
+        head = item % p.heads;
+        const int rest = item / p.heads;
+        const int b = rest / pairs_per_img;
+        qtile0 = 2 * (rest - b * pairs_per_img);
+        img_row0 = b * p.H;
+    };
+    const int nkb = p.nkb;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int n = 0;
+            uint32_t kload = 0, vload = 0;
+            auto load_tile = [&](uint32_t dst, uint32_t fb, int head, int which, int row) {
+                tma_load_5d(dst, &tmap_main, fb, 0, head, which, 0, row);
+                tma_load_5d(dst + kGTileMain, &tmap_tail, fb, 64, head, which, 0, row);
+            };
+            auto load_k = [&](int head, int img_row0, int j) {
+                const uint32_t s = kload % kGStages;
+                mbar_wait(k_empty + 8 * s, ((kload / kGStages) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(k_full + 8 * s, kGTile);
+                load_tile(base + kGOffK + s * kGTile, k_full + 8 * s, head, 1, img_row0 + j * p.rows_per_tile);
+                ++kload;
+            };
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+                int head, img_row0, qtile0;
+                decode(item, head, img_row0, qtile0);
+                mbar_wait(q_empty, (n & 1u) ^ 1u);
+                mbar_arrive_expect_tx(q_full, 2 * kGTile);
+                for (int r = 0; r < 2; ++r) {
+                    tma_load_5d(base + kGOffQ + r * kGTileMain, &tmap_main, q_full, 0, head, 0, 0,
+                                img_row0 + (qtile0 + r) * p.rows_per_tile);
+                    tma_load_5d(base + kGOffQ + 2 * kGTileMain + r * kGTileTail, &tmap_tail, q_full, 64, head, 0, 0,
+                                img_row0 + (qtile0 + r) * p.rows_per_tile);
+                }
+                for (int j = 0; j < nkb; ++j) load_k(head, img_row0, j);  // pass A
+                for (int j = 0; j < nkb; ++j) {                            // pass B: K_j then V_j, in consumption order
+                    load_k(head, img_row0, j);
+                    const uint32_t s = vload % kGStages;
+                    mbar_wait(v_empty + 8 * s, ((vload / kGStages) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(v_full + 8 * s, kGTile);
+                    load_tile(base + kGOffV + s * kGTile, v_full + 8 * s, head, 2, img_row0 + j * p.rows_per_tile);
+                    ++vload;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (event driven, one state machine per region) =====================
+        if (lane == 0) {
+#ifdef SPG_FP16
+            constexpr uint32_t kFmt = 0u;
+#else
+            constexpr uint32_t kFmt = 1u;
+#endif
+            constexpr uint32_t kIdescBase = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((128u >> 4) << 24);
+            constexpr uint32_t idesc_s = kIdescBase | ((128u >> 3) << 17);                      // N = 128 keys
+            constexpr uint32_t idesc_pv64 = kIdescBase | (1u << 16) | ((64u >> 3) << 17);       // B MN-major
+            constexpr uint32_t idesc_pv16 = kIdescBase | (1u << 16) | ((16u >> 3) << 17);
+            const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+            // per region: item, pass (0 = A, 1 = B), key block, whether the next step is the PV of that block
+            int it_[2] = {0, 0}, ph_[2] = {0, 0}, j_[2] = {0, 0}, need_pv[2] = {0, 0};
+            uint32_t kc[2] = {0, 0}, vc[2] = {0, 0};        // K / V blocks consumed so far (ring position)
+            uint32_t sa_cnt[2] = {0, 0}, pf_cnt[2] = {0, 0}, or_cnt[2] = {0, 0};  // barrier completions consumed
+            int k_uses[kGStages] = {0, 0, 0}, v_uses[kGStages] = {0, 0, 0};
+            int q_uses = 0;
+            uint32_t spins = 0;
+            while (it_[0] < my_items || it_[1] < my_items) {
+                bool progressed = false;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    if (it_[r] >= my_items) continue;
+                    const uint32_t d = tmem_base + 256u * r;
+                    if (!need_pv[r]) {
+                        // ---- S = Q_r K_j^T
+                        const uint32_t ks = kc[r] % kGStages;
+                        if (!mbar_test(k_full + 8 * ks, (kc[r] / kGStages) & 1u)) continue;
+                        if (ph_[r] == 0 && j_[r] == 0 && !mbar_test(q_full, it_[r] & 1u)) continue;
+                        // the region's S columns: pass A block j > 0 and the first block of pass B wait for the warp
+                        // group to have read the previous pass-A scores; everything else is ordered by the MMA pipe
+                        const bool after_a = (ph_[r] == 0 && j_[r] > 0) || (ph_[r] == 1 && j_[r] == 0);
+                        if (after_a && !mbar_test(sa_free + 8 * r, (sa_cnt[r] & 1u))) continue;
+                        if (after_a) ++sa_cnt[r];
+                        tc_fence_after();
+                        const uint32_t qm = base + kGOffQ + r * kGTileMain, qt = base + kGOffQ + 2 * kGTileMain + r * kGTileTail;
+                        const uint32_t km = base + kGOffK + ks * kGTile;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16_ss(d, make_smem_desc(qm + 32u * k, 2, 1024, 16), make_smem_desc(km + 32u * k, 2, 1024, 16),
+                                         idesc_s, k != 0);
+                        umma_bf16_ss(d, make_smem_desc(qt, 6, 256, 16), make_smem_desc(km + kGTileMain, 6, 256, 16), idesc_s, 1);
+                        umma_commit(s_full + 8 * r);
+                        if (++k_uses[ks] == 2) {
+                            k_uses[ks] = 0;
+                            umma_commit(k_empty + 8 * ks);  // both query tiles have used this K block
+                        }
+                        ++kc[r];
+                        if (ph_[r] == 1) {
+                            need_pv[r] = 1;
+                            if (j_[r] == nkb - 1 && ++q_uses == 2) {
+                                q_uses = 0;
+                                umma_commit(q_empty);  // last S of the item issued for both tiles
+                            }
+                        } else if (++j_[r] == nkb) {
+                            ph_[r] = 1;
+                            j_[r] = 0;
+                        }
+                        progressed = true;
+                    } else {
+                        // ---- O_r += P_j V_j
+                        const uint32_t vs = vc[r] % kGStages;
+                        if (!mbar_test(v_full + 8 * vs, (vc[r] / kGStages) & 1u)) continue;
+                        if (!mbar_test(p_full + 8 * r, pf_cnt[r] & 1u)) continue;
+                        // the first PV of an item overwrites O: the previous item's epilogue must have read it
+                        if (j_[r] == 0 && it_[r] > 0 && !mbar_test(o_read + 8 * r, or_cnt[r] & 1u)) continue;
+                        if (j_[r] == 0 && it_[r] > 0) ++or_cnt[r];
+                        ++pf_cnt[r];
+                        tc_fence_after();
+                        const uint32_t vm = base + kGOffV + vs * kGTile;
+#pragma unroll 4
+                        for (int k = 0; k < kGKeys / 16; ++k) {
+                            const uint32_t acc = (j_[r] | k) != 0;
+                            umma_ts(d + 128, d + 8u * k, make_smem_desc(vm + 2048u * k, 2, 1024, 16), idesc_pv64, acc);
+                            umma_ts(d + 192, d + 8u * k, make_smem_desc(vm + kGTileMain + 512u * k, 6, 256, 16), idesc_pv16, acc);
+                        }
+                        if (j_[r] == nkb - 1) umma_commit(pv_done + 8 * r);
+                        if (++v_uses[vs] == 2) {
+                            v_uses[vs] = 0;
+                            umma_commit(v_empty + 8 * vs);
+                        }
+                        ++vc[r];
+                        need_pv[r] = 0;
+                        if (++j_[r] == nkb) {
+                            j_[r] = 0;
+                            ph_[r] = 0;
+                            ++it_[r];
+                        }
+                        progressed = true;
+                    }
+                }
+                if (progressed) {
+                    spins = 0;
+                } else if (++spins > (1u << 27)) {
+                    printf("spg: attention_tc_global MMA issuer stuck block=%d items=(%d,%d) pass=(%d,%d) j=(%d,%d)\n",
+                           (int)blockIdx.x, it_[0], it_[1], ph_[0], ph_[1], j_[0], j_[1]);
+                    __trap();
+                }
+            }
+        }
+    } else {
+        // ============ softmax + epilogue: warps 2..5 own query tile 0, warps 6..9 query tile 1; thread == query row
+        const int r = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + 256u * r;
+        uint32_t s_cnt = 0;  // s_full completions consumed
+        int n = 0;
+        for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
+            int head, img_row0, qtile0;
+            decode(item, head, img_row0, qtile0);
+            uint32_t ra[32], rb[32];
+            // ---- pass A: running maximum of the raw scores over all key blocks
+            float mx = -INFINITY;
+            for (int j = 0; j < nkb; ++j) {
+                mbar_wait(s_full + 8 * r, s_cnt & 1u);
+                ++s_cnt;
+                tc_fence_after();
+                tmem_ld32(lane_addr, ra);
+                tmem_ld32(lane_addr + 32, rb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+                tmem_ld32(lane_addr + 64, ra);
+                tmem_ld32(lane_addr + 96, rb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sa_free + 8 * r);
+            }
+            const float m = mx * p.scale_log2e;
+            // ---- pass B: probabilities of every key block, packed in place; O accumulates in TMEM
+            float sum0 = 0.f, sum1 = 0.f;
+            auto exp_pack_store = [&](const uint32_t (&raw)[32], int c) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float p0, p1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2e, -m)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2e, -m)));
+                    sum0 += p0;
+                    sum1 += p1;
+                    pk[i] = pack2(p0, p1);
+                }
+                tmem_st16(lane_addr + 16 * c, pk);
+            };
+            for (int j = 0; j < nkb; ++j) {
+                mbar_wait(s_full + 8 * r, s_cnt & 1u);
+                ++s_cnt;
+                tc_fence_after();
+                tmem_ld32(lane_addr, ra);
+                tmem_ld_wait();
+                tmem_ld32(lane_addr + 32, rb);
+                exp_pack_store(ra, 0);
+                tmem_ld_wait();
+                tmem_ld32(lane_addr + 64, ra);
+                exp_pack_store(rb, 1);
+                tmem_ld_wait();
+                tmem_ld32(lane_addr + 96, rb);
+                exp_pack_store(ra, 2);
+                tmem_ld_wait();
+                exp_pack_store(rb, 3);
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full + 8 * r);
+            }
+            // ---- epilogue: O / sum -> out[token, head*72 .. +72)
+            const long long tok = (static_cast<long long>(img_row0) * p.W) + static_cast<long long>(qtile0 + r) * 128 + row;
+            uint4* dst = reinterpret_cast<uint4*>(p.out + tok * p.D + head * kHd);
+            mbar_wait(pv_done + 8 * r, n & 1u);
+            tc_fence_after();
+            const float inv = 1.f / (sum0 + sum1);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                uint32_t raw[16];
+                tmem_ld16(lane_addr + 128 + 16 * c, raw);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * inv;
+                dst[2 * c] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                if (c < 4)
+                    dst[2 * c + 1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]),
+                                                pack2(v[14], v[15]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_read + 8 * r);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace spg
 
@@ -315,8 +644,33 @@ extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, in
                                            int window, int q_pool, spg_stream_t stream) {
     using namespace spg;
     SPG_CHECK_ARG(qkv && out, "null pointer");
+    if (window == 0 && !q_pool && D == heads * kHd && H == W && (W == 32 || W == 64 || W == 128) && (H * W) % 256 == 0) {
+        // global attention: two-pass tcgen05 kernel over 128-key blocks
+        AttnGlobalParams g{};
+        g.out = static_cast<h16*>(out);
+        g.B = B; g.H = H; g.W = W; g.D = D; g.heads = heads;
+        g.rows_per_tile = 128 / W;
+        g.tiles_per_img = H * W / 128;
+        g.nkb = g.tiles_per_img;
+        g.items = B * heads * (g.tiles_per_img / 2);
+        g.reverse = traversal_reversed() ? 1 : 0;
+        g.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
+        CUtensorMap gm, gt;
+        if (int rc = make_tmap_qkv_5d(&gm, qkv, static_cast<uint64_t>(B) * H, W, heads, 64, W, g.rows_per_tile, 128)) return rc;
+        if (int rc = make_tmap_qkv_5d(&gt, qkv, static_cast<uint64_t>(B) * H, W, heads, 16, W, g.rows_per_tile, 32)) return rc;
+        static bool g_attr_set = false;
+        if (!g_attr_set) {
+            SPG_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemG));
+            g_attr_set = true;
+        }
+        const int ggrid = g.items < sm_count() ? g.items : sm_count();
+        SPG_CHECK_CUDA((launch_pdl(attention_tc_global_kernel, ggrid, kThreadsTc, kSmemG, static_cast<cudaStream_t>(stream), gm, gt, g)));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        SPG_CHECK_LAUNCH();
+        return SPG_OK;
+    }
     if (window != kWs || q_pool || H % kWs || W % kWs || D != heads * kHd)
-        return fail(SPG_ERR_UNSUPPORTED, "tcgen05 attention covers 16x16 windows without query pooling");
+        return fail(SPG_ERR_UNSUPPORTED, "tcgen05 attention covers 16x16 windows and global attention, without query pooling");
     AttnTcParams p{};
     p.out = static_cast<h16*>(out);
     p.B = B; p.H = H; p.W = W; p.D = D; p.heads = heads;

@@ -171,7 +171,8 @@ def _ref_attention(qkv, B, H, D, heads, ws, qpool):
     (16, 4, 4, False),    # stage 2
     (16, 8, 4, True),     # block 8: 4 pooled queries x 16 keys (CUDA-core path)
     (32, 8, 16, False),   # stage 3 windows
-    (32, 8, 0, False),    # stage 3 global, 1024 keys (4 staged passes)
+    (32, 8, 0, False),    # stage 3 global, 1024 keys: two-pass tcgen05 kernel, 8 key blocks of 128
+    (64, 8, 0, False),    # stage 3 global at 1024x1024 input: 4096 keys, 2 grid rows per 128-token tile
     (32, 16, 16, True),   # block 44
     (16, 16, 8, False),   # stage 4
 ])
