@@ -311,7 +311,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
 // Global attention (window == 0: the three global blocks of stage 3, 1024 keys at 512^2 and 4096 at 1024^2) on
 // tcgen05 / TMEM.  A work item is (image, head, 256 consecutive queries) = two 128-query tiles, one TMEM region each;
 // the keys are streamed in blocks of 128 through two 3-stage TMA rings (K and V).  The softmax is exact and two-pass:
-//   pass A  for every key block: S = Q K_j^T (SS-MMA, N = 128) -> the row's warp group folds it into the running maximum;
+//   pass A  for every PAIR of key blocks: S = Q [K_j | K_j+1]^T (SS-MMAs, 256 columns = the whole region, O is not live
+//           yet) -> the row's warp group folds it into the running maximum: one handshake per 256 keys (a handshake
+//           MMA -> barrier -> TMEM load -> barrier costs ~1.5 us whatever the tile size, so fewer, larger units win:
+//           64-key units with double-buffered S measured 803 us against 486 us for 128-key units);
 //   pass B  for every key block: S again -> p = 2^(s * scale - m) written back to TMEM as packed 16-bit pairs over the
 //           consumed S columns -> O += P V_j (TS-MMA, V MN-major) accumulating in TMEM across ALL key blocks.
 // Recomputing S costs 1.5x the MMA work of an online softmax but needs no rescaling of O in TMEM, and the tensor pipe
@@ -460,14 +463,52 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
                 for (int r = 0; r < 2; ++r) {
                     if (it_[r] >= my_items) continue;
                     const uint32_t d = tmem_base + 256u * r;
-                    if (!need_pv[r]) {
-                        // ---- S = Q_r K_j^T
+                    if (!need_pv[r] && ph_[r] == 0) {
+                        // ---- pass A: S = Q_r [K_j | K_j+1]^T, 256 keys per handshake, over the WHOLE region (O is not
+                        // live in this pass; the previous item's epilogue must have read it: o_read)
+                        const uint32_t ks0 = kc[r] % kGStages, ks1 = (kc[r] + 1) % kGStages;
+                        if (!mbar_test(k_full + 8 * ks0, (kc[r] / kGStages) & 1u)) continue;
+                        if (!mbar_test(k_full + 8 * ks1, ((kc[r] + 1) / kGStages) & 1u)) continue;
+                        if (j_[r] == 0 && !mbar_test(q_full, it_[r] & 1u)) continue;
+                        if (j_[r] == 0 && it_[r] > 0 && !mbar_test(o_read + 8 * r, or_cnt[r] & 1u)) continue;
+                        if (j_[r] > 0 && !mbar_test(sa_free + 8 * r, sa_cnt[r] & 1u)) continue;
+                        if (j_[r] == 0 && it_[r] > 0) ++or_cnt[r];
+                        if (j_[r] > 0) ++sa_cnt[r];
+                        tc_fence_after();
+                        const uint32_t qm = base + kGOffQ + r * kGTileMain, qt = base + kGOffQ + 2 * kGTileMain + r * kGTileTail;
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            const uint32_t km = base + kGOffK + (hb ? ks1 : ks0) * kGTile;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16_ss(d + 128u * hb, make_smem_desc(qm + 32u * k, 2, 1024, 16),
+                                             make_smem_desc(km + 32u * k, 2, 1024, 16), idesc_s, k != 0);
+                            umma_bf16_ss(d + 128u * hb, make_smem_desc(qt, 6, 256, 16), make_smem_desc(km + kGTileMain, 6, 256, 16),
+                                         idesc_s, 1);
+                        }
+                        umma_commit(s_full + 8 * r);
+                        if (++k_uses[ks0] == 2) {
+                            k_uses[ks0] = 0;
+                            umma_commit(k_empty + 8 * ks0);
+                        }
+                        if (++k_uses[ks1] == 2) {
+                            k_uses[ks1] = 0;
+                            umma_commit(k_empty + 8 * ks1);
+                        }
+                        kc[r] += 2;
+                        j_[r] += 2;
+                        if (j_[r] == nkb) {
+                            ph_[r] = 1;
+                            j_[r] = 0;
+                        }
+                        progressed = true;
+                    } else if (!need_pv[r]) {
+                        // ---- pass B: S = Q_r K_j^T
                         const uint32_t ks = kc[r] % kGStages;
                         if (!mbar_test(k_full + 8 * ks, (kc[r] / kGStages) & 1u)) continue;
-                        if (ph_[r] == 0 && j_[r] == 0 && !mbar_test(q_full, it_[r] & 1u)) continue;
                         // the region's S columns: pass A block j > 0 and the first block of pass B wait for the warp
                         // group to have read the previous pass-A scores; everything else is ordered by the MMA pipe
-                        const bool after_a = (ph_[r] == 0 && j_[r] > 0) || (ph_[r] == 1 && j_[r] == 0);
+                        const bool after_a = j_[r] == 0;  // first block of pass B: the last pass-A scores have been read
                         if (after_a && !mbar_test(sa_free + 8 * r, (sa_cnt[r] & 1u))) continue;
                         if (after_a) ++sa_cnt[r];
                         tc_fence_after();
@@ -484,15 +525,10 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
                             umma_commit(k_empty + 8 * ks);  // both query tiles have used this K block
                         }
                         ++kc[r];
-                        if (ph_[r] == 1) {
-                            need_pv[r] = 1;
-                            if (j_[r] == nkb - 1 && ++q_uses == 2) {
-                                q_uses = 0;
-                                umma_commit(q_empty);  // last S of the item issued for both tiles
-                            }
-                        } else if (++j_[r] == nkb) {
-                            ph_[r] = 1;
-                            j_[r] = 0;
+                        need_pv[r] = 1;
+                        if (j_[r] == nkb - 1 && ++q_uses == 2) {
+                            q_uses = 0;
+                            umma_commit(q_empty);  // last S of the item issued for both tiles
                         }
                         progressed = true;
                     } else {
@@ -500,10 +536,7 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
                         const uint32_t vs = vc[r] % kGStages;
                         if (!mbar_test(v_full + 8 * vs, (vc[r] / kGStages) & 1u)) continue;
                         if (!mbar_test(p_full + 8 * r, pf_cnt[r] & 1u)) continue;
-                        // the first PV of an item overwrites O: the previous item's epilogue must have read it
-                        if (j_[r] == 0 && it_[r] > 0 && !mbar_test(o_read + 8 * r, or_cnt[r] & 1u)) continue;
-                        if (j_[r] == 0 && it_[r] > 0) ++or_cnt[r];
-                        ++pf_cnt[r];
+                        ++pf_cnt[r];  // (O was released by the previous item's epilogue before pass A started)
                         tc_fence_after();
                         const uint32_t vm = base + kGOffV + vs * kGTile;
 #pragma unroll 4
@@ -550,20 +583,18 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
             uint32_t ra[32], rb[32];
             // ---- pass A: running maximum of the raw scores over all key blocks
             float mx = -INFINITY;
-            for (int j = 0; j < nkb; ++j) {
+            for (int j = 0; j < nkb; j += 2) {  // 256 keys per handshake
                 mbar_wait(s_full + 8 * r, s_cnt & 1u);
                 ++s_cnt;
                 tc_fence_after();
-                tmem_ld32(lane_addr, ra);
-                tmem_ld32(lane_addr + 32, rb);
-                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
-                tmem_ld32(lane_addr + 64, ra);
-                tmem_ld32(lane_addr + 96, rb);
-                tmem_ld_wait();
+                for (int c = 0; c < 256; c += 64) {
+                    tmem_ld32(lane_addr + c, ra);
+                    tmem_ld32(lane_addr + c + 32, rb);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sa_free + 8 * r);
