@@ -369,6 +369,7 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
         if (tc_env && window == 16 && !q_pool && H % 16 == 0 && W % 16 == 0 && D == heads * 72)
             return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, stream);
         // global blocks (window == 0) on a 32 / 64 / 128-wide token grid: two-pass tcgen05 kernel (SPG_ATTN_TC=2: windows only)
+        // (at every batch size: an image's result must not depend on the batch it is in, bit for bit)
         if (tc_env == 1 && window == 0 && !q_pool && H == W && (W == 32 || W == 64 || W == 128) && D == heads * 72)
             return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, stream);
     }

@@ -167,6 +167,17 @@ def window_attention(qkv: torch.Tensor, out: torch.Tensor, B: int, H: int, W: in
     _lib.check(rc, "spg_window_attention_h16", dn)
 
 
+def window_attention_tc(qkv: torch.Tensor, out: torch.Tensor, B: int, H: int, W: int, D: int, heads: int, window: int,
+                        q_pool: bool) -> None:
+    """The tcgen05 / TMEM attention kernels directly (16x16 windows or global, no query pooling); `window_attention`
+    dispatches to them whenever they apply.  See spg_window_attention_tc_h16."""
+    lib, dn = _lib_for(qkv)
+    _lib.flip_direction()
+    rc = lib.spg_window_attention_tc_h16(_ptr(qkv, H16, "qkv"), _ptr(out, H16, "out"), B, H, W, D, heads, window,
+                                         int(q_pool), _stream())
+    _lib.check(rc, "spg_window_attention_tc_h16", dn)
+
+
 def upsample_concat(src0: torch.Tensor, src1: Optional[torch.Tensor], out: torch.Tensor) -> None:
     B, Ho, Wo, _ = out.shape
     _, h0, w0, c0 = src0.shape

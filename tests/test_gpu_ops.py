@@ -366,3 +366,16 @@ def test_layernorm_folded_into_producer_and_consumer(ops, M, C, N2):
         if act == ops.ACT_GELU:
             ref = F.gelu(ref)
         _close(out, ref, 3e-2, 1.5e-2)
+
+
+@pytest.mark.parametrize("B,H,heads,ws", [(2, 32, 8, 16), (2, 32, 8, 0), (1, 64, 8, 0), (20, 32, 8, 0)])
+def test_tcgen05_attention_kernels_directly(ops, B, H, heads, ws):
+    """The tcgen05 / TMEM kernels through their own entry point: 16x16 windows, global 1024 keys, global 4096 keys (2 grid rows per 128-token tile), and a
+    batch with more items than SMs (persistent loop over items, ring wrap-around)."""
+    D = heads * 72
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + H + ws)
+    qkv = _bf(torch.randn(B * H * H, 3 * D, device="cuda", generator=g) * 1.5)
+    out = torch.full((B * H * H, D), float("nan"), device="cuda", dtype=H16)
+    ops.window_attention_tc(qkv, out, B, H, H, D, heads, ws, False)
+    ref = _ref_attention(qkv, B, H, D, heads, ws, False)
+    _close(out.view(B, H, H, D), ref, 2e-2, 2e-2)
