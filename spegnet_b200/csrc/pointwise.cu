@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
         for (int i = 0; i < MAXV; ++i) {
             const int j = sub + LPR * i;
             if (ok && j < nvec) {
-                v[i] = xr[j];
+                v[i] = __ldcs(xr + j);  // streaming: this is the last read of the fp32 row before the block's GEMMs; keep L2 for y
                 s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
             }
         }
