@@ -18,4 +18,7 @@ Contents
 ``sod_metrics``  numpy/scipy restatement of the ``py_sod_metrics`` scores used by utils/metrics.py
                  (third-party ``pysodmetrics``, unpinned, absent -- **parity unpinned**; pinned only by
                  analytic known-answer tests).
+``preprocess``   CODImageProcessor.process_image from the decoded RGB array on (utils/image_processor.py:114-134) and
+                 the prediction resize of engine/predictor.py:350-365 -- pinned bit-exact against the reference
+                 class run on PNG fixtures (tests/golden/make_golden_preprocess.py -> preprocess.npz).
 """
