@@ -10,7 +10,7 @@ Everything here works on CPU tensors with the ``gloo`` backend too (tests/test_s
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence
+from typing import Callable, List, Sequence
 
 import torch
 import torch.distributed as dist
