@@ -9,7 +9,8 @@
  *
  * Conventions (all functions):
  *   - plain device pointers + sizes, caller-owned memory, NO allocation, NO synchronisation and NO
- *     global state inside; work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *     global state inside (the only process-wide datum is the diagnostic launch counter); work is enqueued on
+ *     `launch->stream` with the per-call flags of `launch` (spg_launch_t below).
  *   - return SPG_OK (0) or a negative SPG_ERR_* code; spg_last_error() gives the text (thread-local).
  *   - activations are NHWC ("tokens x channels") in the library's 16-bit storage type "h16" unless
  *     stated: IEEE half in libspegnet_b200_fp16.so, bfloat16 in libspegnet_b200_bf16.so (same sources,
@@ -41,7 +42,24 @@ extern "C" {
 #define SPG_H16 0 /* the library's 16-bit storage type (fp16 or bf16, see above) */
 #define SPG_F32 1
 
-typedef void* spg_stream_t; /* cudaStream_t */
+/*
+ * Per-call launch descriptor, the last argument of every entry point that enqueues work.  NULL = the default stream
+ * with no flags.  Nothing about a launch is process-global: two host threads / streams / models cannot disturb each
+ * other, and a CUDA graph captures exactly the flags its calls were made with.
+ *   SPG_LAUNCH_PDL      the kernels carry cudaLaunchAttributeProgrammaticStreamSerialization and overlap their
+ *                       global-data-free prologue with the tail of their predecessor in the stream
+ *                       (griddepcontrol.launch_dependents / wait); pays for small batches (launch-latency regime).
+ *   SPG_LAUNCH_REVERSE  walk rows / tiles / work items in descending order.  Consecutive kernels of the forward are
+ *                       producer -> consumer pairs over tensors larger than the 126 MB L2; a host that alternates this
+ *                       flag launch by launch lets each consumer start on the rows its producer wrote last.  Honoured
+ *                       by the GEMM / conv engine, LayerNorm and the attention kernels; results do not depend on it.
+ */
+#define SPG_LAUNCH_PDL 1u
+#define SPG_LAUNCH_REVERSE 2u
+typedef struct spg_launch {
+    void* stream;   /* cudaStream_t */
+    unsigned flags; /* SPG_LAUNCH_* */
+} spg_launch_t;
 
 /* Library version (major*10000 + minor*100 + patch). */
 int spg_version(void);
@@ -51,13 +69,6 @@ const char* spg_last_error(void);
 int spg_device_check(void);
 /* 1 if this build stores activations / weights as IEEE fp16, 0 if bfloat16. */
 int spg_half_is_fp16(void);
-/* Programmatic dependent launch for the kernels enqueued from now on (1 = on, the default): every kernel then carries
- * cudaLaunchAttributeProgrammaticStreamSerialization and overlaps its global-data-free prologue with the tail of its
- * predecessor (griddepcontrol.launch_dependents / wait).  The environment variable SPG_PDL=0|1 overrides it. */
-void spg_set_pdl(int on);
-/* Traversal direction of the kernels enqueued from now on (0 = ascending rows / tiles, 1 = descending).  The host
- * alternates it launch by launch so that each consumer starts on the rows its producer wrote last (still in L2). */
-void spg_set_reverse(int reversed);
 /* Number of kernels this library has launched since load / since the last reset (all threads). */
 long long spg_launch_count(void);
 void spg_launch_count_reset(void);
@@ -106,7 +117,7 @@ typedef struct spg_epilogue {
  * K and N may be any multiple of 8 / 16; K tails are zero-filled by TMA.
  */
 int spg_linear_h16(const void* A, const void* W, int M, int N, int K, const spg_epilogue_t* ep,
-                    spg_stream_t stream);
+                    const spg_launch_t* launch);
 
 /*
  * 3x3, stride 1, zero-pad 1 convolution as an implicit GEMM: x is NHWC bf16 [B,H,W,Cin]
@@ -116,7 +127,7 @@ int spg_linear_h16(const void* A, const void* W, int M, int N, int K, const spg_
  * (models/object_detection.py:115-123,150-152,193-198,230-236).
  */
 int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, int Cout,
-                     const spg_epilogue_t* ep, spg_stream_t stream);
+                     const spg_epilogue_t* ep, const spg_launch_t* launch);
 
 /*
  * Bilinear x2 upsample (align_corners=False) FUSED into the 3x3 convolution that consumes it:
@@ -136,18 +147,18 @@ int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, 
  * (`up2_phase_weights`), pinned against F.interpolate + F.conv2d in tests/test_host.py and tests/test_gpu_ops.py.
  */
 int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const float* corr, int B, int H, int W, int Cin, int Cout,
-                        const float* bias4, void* out, spg_stream_t stream);
+                        const float* bias4, void* out, const spg_launch_t* launch);
 
 /* Left operand of the border-column correction GEMM above: out [2][B*H][9*C] bf16,
  * out[s][b*H+y][(cls*3+dy)*C + c] = x[b, y+dy-1, s ? W-1 : 0, c] in the block of y's row class, zero elsewhere. */
-int spg_up2_border_gather_h16(const void* x, void* out, int B, int H, int W, int C, spg_stream_t stream);
+int spg_up2_border_gather_h16(const void* x, void* out, int B, int H, int W, int C, const spg_launch_t* launch);
 
 /*
  * y[M,C] (bf16) = LayerNorm(x[M,C] (fp32 residual stream)) * gamma + beta, eps as given (1e-6 in Hiera).
  * Replaces blocks.{i}.norm1 / norm2 (HF:modeling_sam2.py:495,528).  C % 4 == 0, C <= 1152.
  */
 int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
-                           float eps, spg_stream_t stream);
+                           float eps, const spg_launch_t* launch);
 
 /*
  * im2col for the 7x7 / stride 4 / pad 3 patch embedding: x fp32 NCHW [B,3,S,S] (16-byte aligned) -> cols bf16
@@ -156,14 +167,14 @@ int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta,
  * the positional embedding as a broadcast residual (res_rows = (S/4)^2).
  * Replaces PatchEmbed's Conv2d(3,144,7,4,3) + permute (HF:modeling_sam2.py:138-148).
  */
-int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_stream_t stream);
+int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, const spg_launch_t* launch);
 
 /* 2x2 / stride-2 max pool of an fp32 NHWC map: the pooled shortcut of blocks 2 / 8 / 44
  * (do_pool(self.proj(x)), HF:modeling_sam2.py:271-279,499-500). */
-int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W, int C, spg_stream_t stream);
+int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W, int C, const spg_launch_t* launch);
 
 /* fp32 -> bf16 copy (stage outputs of the residual stream become GEMM operands of the head). n % 8 == 0. */
-int spg_cast_f32_h16(const float* x, void* y, long long n, spg_stream_t stream);
+int spg_cast_f32_h16(const float* x, void* y, long long n, const spg_launch_t* launch);
 
 /*
  * Multi-head attention over non-overlapping window x window token tiles of the NHWC grid [B,H,W]
@@ -174,7 +185,7 @@ int spg_cast_f32_h16(const float* x, void* y, long long n, spg_stream_t stream);
  * (HF:modeling_sam2.py:307-345,378-438,503-525).
  */
 int spg_window_attention_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads, int window,
-                              int q_pool, spg_stream_t stream);
+                              int q_pool, const spg_launch_t* launch);
 
 /*
  * The tcgen05 / TMEM implementation of the same operation for window == 16 without query pooling (the 32 windowed
@@ -182,7 +193,7 @@ int spg_window_attention_h16(const void* qkv, void* out, int B, int H, int W, in
  * TMEM.  spg_window_attention_h16 dispatches to it automatically; other geometries return SPG_ERR_UNSUPPORTED.
  */
 int spg_window_attention_tc_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads, int window,
-                                int q_pool, spg_stream_t stream);
+                                int q_pool, const spg_launch_t* launch);
 
 /*
  * out[b,y,x,:] = concat(bilinear(src0 [B,h0,w0,c0]), bilinear(src1 [B,h1,w1,c1])) resized to Ho x Wo,
@@ -190,7 +201,7 @@ int spg_window_attention_tc_h16(const void* qkv, void* out, int B, int H, int W,
  * DecoderBlock.forward (models/object_detection.py:219-227).  Channel counts % 8 == 0.
  */
 int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0, const void* src1, int h1, int w1, int c1,
-                             void* out, int B, int Ho, int Wo, spg_stream_t stream);
+                             void* out, int B, int Ho, int Wo, const spg_launch_t* launch);
 
 /*
  * CFI fusion tail.  Conv1x1(concat(f2, up2(f3), up4(f4))) is linear, so the three per-scale products
@@ -201,11 +212,11 @@ int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0, const void
  * with 4x fewer MACs and no 2016-channel concat; row_sums feeds the SE squeeze (:147).
  */
 int spg_fusion_combine(const float* g2, const float* g3, const float* g4, const float* bias, void* fused,
-                       float* row_sums, int B, int Hs, int C, spg_stream_t stream);
+                       float* row_sums, int B, int Hs, int C, const spg_launch_t* launch);
 
 /* row_sums[b,y,:] = sum_x x[b,y,x,:] for a bf16 NHWC map (AdaptiveAvgPool2d(1) partials,
  * models/feature_integration.py:336,401). */
-int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C, spg_stream_t stream);
+int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C, const spg_launch_t* launch);
 
 /*
  * Pooled-vector MLP, one CTA per image.  mean = sum_rows(row_sums) / count, then
@@ -213,10 +224,10 @@ int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C,
  *   W2 == NULL: out[b, R] = relu(W1[R,C] @ mean + b1)          (e-ASPP global branch, :335-345,401)
  */
 int spg_pooled_mlp(const float* row_sums, int rows, int count, const float* W1, const float* b1, int R,
-                   const float* W2, float* out, int B, int C, spg_stream_t stream);
+                   const float* W2, float* out, int B, int C, const spg_launch_t* launch);
 
 /* x[b,p,c] *= gate[b,c] in place, bf16 NHWC (SE rescale, models/feature_integration.py:151). */
-int spg_scale_channels_h16(void* x, const float* gate, int B, int HW, int C, spg_stream_t stream);
+int spg_scale_channels_h16(void* x, const float* gate, int B, int HW, int C, const spg_launch_t* launch);
 
 /*
  * e-ASPP core in one pass over x bf16 [B,H,W,128]: four depth-wise dilated 3x3 branches (+BN+ReLU),
@@ -227,7 +238,7 @@ int spg_scale_channels_h16(void* x, const float* gate, int B, int HW, int C, spg
  */
 int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, const float* gvec, const float* wf,
                        const float* wf_bias, void* y, int B, int H, int W, const int* dilations,
-                       spg_stream_t stream);
+                       const spg_launch_t* launch);
 
 /*
  * Mask quantisation of the reference's metric wrapper on the GPU (utils/metrics.py:205-210): mask = uint8(
@@ -238,7 +249,7 @@ int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, con
  * ranks all_gather in the sharded evaluation (8 x 4 bytes per image instead of the mask).
  */
 int spg_mask_stats_u8(const float* logits, const unsigned char* gt, unsigned char* mask, unsigned* stats, int B,
-                      int HW, int double_sigmoid, spg_stream_t stream);
+                      int HW, int double_sigmoid, const spg_launch_t* launch);
 
 /*
  * The five camouflaged-object scores of the reference's metric wrapper, per image, on the GPU in fp64:
@@ -256,10 +267,10 @@ int spg_mask_stats_u8(const float* logits, const unsigned char* gt, unsigned cha
  */
 size_t spg_sod_workspace_bytes(int B, int H, int W);
 int spg_sod_gt_prepare_u8(const unsigned char* gt, int B, int H, int W, int* nearest, unsigned long long* gt_stats,
-                          void* workspace, size_t ws_bytes, spg_stream_t stream);
+                          void* workspace, size_t ws_bytes, const spg_launch_t* launch);
 int spg_sod_scores_u8(const unsigned char* pred, const unsigned char* gt, const int* nearest,
                       const unsigned long long* gt_stats, int B, int H, int W, double* scores, void* workspace,
-                      size_t ws_bytes, spg_stream_t stream);
+                      size_t ws_bytes, const spg_launch_t* launch);
 
 /*
  * Image preprocessing of the reference on the GPU: CODImageProcessor.process_image (utils/image_processor.py:114-134):
@@ -271,7 +282,7 @@ int spg_sod_scores_u8(const unsigned char* pred, const unsigned char* gt, const 
  */
 size_t spg_preprocess_workspace_bytes(int H, int W, int S);
 int spg_preprocess_rgb_u8(const unsigned char* img, int H, int W, float* out, int S, const float* mean3,
-                          const float* std3, void* workspace, size_t ws_bytes, spg_stream_t stream);
+                          const float* std3, void* workspace, size_t ws_bytes, const spg_launch_t* launch);
 
 /*
  * dst[b] = F.interpolate(src[b], size=(Ho,Wo), mode='bilinear', align_corners=False) for fp32 maps [B,Hi,Wi], followed
@@ -279,10 +290,10 @@ int spg_preprocess_rgb_u8(const unsigned char* img, int H, int W, float* out, in
  * ground-truth size (engine/predictor.py:350-365, engine/evaluator.py:539-554).
  */
 int spg_resize_bilinear_f32(const float* src, int B, int Hi, int Wi, float* dst, int Ho, int Wo, int apply_sigmoid,
-                            spg_stream_t stream);
+                            const spg_launch_t* launch);
 
 /* bf16 NHWC [B,HW,C] -> fp32 NCHW [B,C,HW] (materialises `features` entries of the output dict on demand). */
-int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream);
+int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, const spg_launch_t* launch);
 
 #ifdef __cplusplus
 }

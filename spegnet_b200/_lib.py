@@ -34,6 +34,14 @@ class Epilogue(C.Structure):
     ]
 
 
+class Launch(C.Structure):
+    """Mirror of ``spg_launch_t``: the per-call launch descriptor (stream + SPG_LAUNCH_* flags)."""
+
+    _fields_ = [("stream", C.c_void_p), ("flags", C.c_uint)]
+
+
+LAUNCH_PDL, LAUNCH_REVERSE = 1, 2
+
 _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
@@ -68,8 +76,6 @@ _SPECIAL = {
     "spg_last_error": ([], C.c_char_p),
     "spg_launch_count": ([], C.c_longlong),
     "spg_launch_count_reset": ([], None),
-    "spg_set_pdl": ([_I], None),
-    "spg_set_reverse": ([_I], None),
     "spg_sod_workspace_bytes": ([_I, _I, _I], C.c_size_t),
     "spg_preprocess_workspace_bytes": ([_I, _I, _I], C.c_size_t),
 }
@@ -131,25 +137,6 @@ def check(rc: int, what: str, dtype: str = DEFAULT_DTYPE) -> None:
         if rc == -1:
             raise ValueError(f"{what}: {msg}")
         raise SpgError(f"{what} failed (code {rc}): {msg}")
-
-
-def set_pdl(on: bool) -> None:
-    """Programmatic dependent launch on / off for every loaded library variant (see spg_set_pdl)."""
-    for lib in _libs.values():
-        lib.spg_set_pdl(int(bool(on)))
-
-
-_direction = 0
-
-
-def flip_direction() -> None:
-    """Alternate the traversal direction for the next launch (see spg_set_reverse); SPG_SNAKE=0 keeps it ascending."""
-    global _direction
-    if os.environ.get("SPG_SNAKE", "1") == "0":
-        return
-    _direction ^= 1
-    for lib in _libs.values():
-        lib.spg_set_reverse(_direction)
 
 
 def launch_count() -> int:

@@ -357,21 +357,21 @@ __global__ void __launch_bounds__(128) tiny_attention_kernel(const AttnParams p)
 }  // namespace spg
 
 extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads,
-                                           int window, int q_pool, spg_stream_t stream);
+                                           int window, int q_pool, const spg_launch_t* launch);
 
 extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads,
-                                         int window, int q_pool, spg_stream_t stream) {
+                                         int window, int q_pool, const spg_launch_t* launch) {
     using namespace spg;
     SPG_CHECK_ARG(qkv && out, "null pointer");
     {
         // 16x16 windows without query pooling (32 of Hiera-L's 48 blocks) run on tcgen05 / TMEM (attention_tc.cu)
         static const int tc_env = [] { const char* e = getenv("SPG_ATTN_TC"); return e ? atoi(e) : 1; }();
         if (tc_env && window == 16 && !q_pool && H % 16 == 0 && W % 16 == 0 && D == heads * 72)
-            return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, stream);
+            return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, launch);
         // global blocks (window == 0) on a 32 / 64 / 128-wide token grid: two-pass tcgen05 kernel (SPG_ATTN_TC=2: windows only)
         // (at every batch size: an image's result must not depend on the batch it is in, bit for bit)
         if (tc_env == 1 && window == 0 && !q_pool && H == W && (W == 32 || W == 64 || W == 128) && D == heads * 72)
-            return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, stream);
+            return spg_window_attention_tc_h16(qkv, out, B, H, W, D, heads, window, q_pool, launch);
     }
     SPG_CHECK_ARG(heads > 0 && D == heads * kHd, "attention is specialised for head_dim 72 (D=%d heads=%d)", D, heads);
     int ws = window;
@@ -389,9 +389,9 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     p.Nk = ws * ws;
     p.Nq = q_pool ? p.Nk / 4 : p.Nk;
     p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
-    p.reverse = traversal_reversed() ? 1 : 0;
+    const LaunchCtx st(launch);
+    p.reverse = st.reverse ? 1 : 0;
     const int nwin = B * p.nwx * p.nwy;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     // tensor-core path: 64-row query tiles over <=256-key passes, or four 16-query windows per CTA
     const bool big = p.Nq % 64 == 0 && p.Nk % 64 == 0 && (p.Nk <= kRowsSmem || p.Nk % kRowsSmem == 0);
     const bool quad = (p.Nq == 16 || p.Nq == 4) && (p.Nk == 16 || p.Nk == 64) && nwin % 4 == 0;
@@ -414,12 +414,12 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     // 600 -> 710 us), so the kernel keeps its natural register count
     p.rows_smem = (p.wpc > 1 ? p.wpc * p.Nk : p.Nk) < kRowsSmem ? (p.wpc > 1 ? p.wpc * p.Nk : p.Nk) : kRowsSmem;
     const int smem = 2 * p.rows_smem * kHd * 2 + 128;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         const int smem_max = 2 * kRowsSmem * kHd * 2 + 128;
         SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
         SPG_CHECK_CUDA(cudaFuncSetAttribute(window_attention_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-        attr_set = true;
+        attr_set.done();
     }
     dim3 grid(p.wpc > 1 ? nwin / p.wpc : nwin * p.qtiles, heads);
     if (p.Nk == 16)

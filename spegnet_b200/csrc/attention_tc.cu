@@ -672,7 +672,7 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
 // tcgen05 path of spg_window_attention_h16 for window == 16 without query pooling (the 32 windowed stage-3 blocks).
 // Returns SPG_ERR_UNSUPPORTED for any other geometry; the caller then uses the generic kernel.
 extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, int H, int W, int D, int heads,
-                                           int window, int q_pool, spg_stream_t stream) {
+                                           int window, int q_pool, const spg_launch_t* launch) {
     using namespace spg;
     SPG_CHECK_ARG(qkv && out, "null pointer");
     if (window == 0 && !q_pool && D == heads * kHd && H == W && (W == 32 || W == 64 || W == 128) && (H * W) % 256 == 0) {
@@ -684,18 +684,18 @@ extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, in
         g.tiles_per_img = H * W / 128;
         g.nkb = g.tiles_per_img;
         g.items = B * heads * (g.tiles_per_img / 2);
-        g.reverse = traversal_reversed() ? 1 : 0;
+        g.reverse = LaunchCtx(launch).reverse ? 1 : 0;
         g.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
         CUtensorMap gm, gt;
         if (int rc = make_tmap_qkv_5d(&gm, qkv, static_cast<uint64_t>(B) * H, W, heads, 64, W, g.rows_per_tile, 128)) return rc;
         if (int rc = make_tmap_qkv_5d(&gt, qkv, static_cast<uint64_t>(B) * H, W, heads, 16, W, g.rows_per_tile, 32)) return rc;
-        static bool g_attr_set = false;
-        if (!g_attr_set) {
+        static PerDeviceOnce g_attr_set;
+        if (g_attr_set.needed()) {
             SPG_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemG));
-            g_attr_set = true;
+            g_attr_set.done();
         }
         const int ggrid = g.items < sm_count() ? g.items : sm_count();
-        SPG_CHECK_CUDA((launch_pdl(attention_tc_global_kernel, ggrid, kThreadsTc, kSmemG, static_cast<cudaStream_t>(stream), gm, gt, g)));
+        SPG_CHECK_CUDA((launch_pdl(attention_tc_global_kernel, ggrid, kThreadsTc, kSmemG, LaunchCtx(launch), gm, gt, g)));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         SPG_CHECK_LAUNCH();
         return SPG_OK;
@@ -707,18 +707,18 @@ extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, in
     p.B = B; p.H = H; p.W = W; p.D = D; p.heads = heads;
     p.nwx = W / kWs; p.nwy = H / kWs;
     p.items = B * p.nwx * p.nwy * heads;
-    p.reverse = traversal_reversed() ? 1 : 0;
+    p.reverse = LaunchCtx(launch).reverse ? 1 : 0;
     p.scale_log2e = 1.4426950408889634f / sqrtf(static_cast<float>(kHd));
     CUtensorMap tmain, ttail;
     if (int rc = make_tmap_qkv_5d(&tmain, qkv, static_cast<uint64_t>(B) * H, W, heads, 64, kWs, 8, 128)) return rc;
     if (int rc = make_tmap_qkv_5d(&ttail, qkv, static_cast<uint64_t>(B) * H, W, heads, 16, kWs, 8, 32)) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
         SPG_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTc));
-        attr_set = true;
+        attr_set.done();
     }
     const int grid = p.items < sm_count() ? p.items : sm_count();
-    SPG_CHECK_CUDA((launch_pdl(attention_tc_kernel, grid, kThreadsTc, kSmemTc, static_cast<cudaStream_t>(stream), tmain, ttail, p)));
+    SPG_CHECK_CUDA((launch_pdl(attention_tc_kernel, grid, kThreadsTc, kSmemTc, LaunchCtx(launch), tmain, ttail, p)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;

@@ -25,25 +25,20 @@ int fail(int code, const char* fmt, ...) {
 }
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    static int cached[128] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& c = cached[dev & 127];
+    if (c == 0) {
+        int n = 0;
+        c = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
     }
-    return cached;
+    return c;
 }
 
-// SPG_PDL=0 / 1 pins the switch; otherwise the host sets it per forward (spg_set_pdl): on in the latency regime
-// (small batches, where the launch / prologue / tail of 371 kernels is a third of the time), off for large batches,
-// where it measured neutral on the device-timed step and -3 % end to end with copy streams active.
-static std::atomic<int> g_pdl{1};
-bool pdl_enabled() {
+int pdl_pinned() {
     static const int pinned = [] { const char* e = getenv("SPG_PDL"); return e == nullptr ? -1 : (atoi(e) != 0 ? 1 : 0); }();
-    return pinned >= 0 ? pinned != 0 : g_pdl.load(std::memory_order_relaxed) != 0;
+    return pinned;
 }
 
 namespace {
@@ -168,14 +163,6 @@ extern "C" int spg_device_check(void) {
     if (major != 10) return spg::fail(SPG_ERR_UNSUPPORTED, "device is sm_%d%d; this library is sm_100a only", major, minor);
     return SPG_OK;
 }
-
-namespace spg {
-static std::atomic<int> g_reverse{0};
-bool traversal_reversed() { return g_reverse.load(std::memory_order_relaxed) != 0; }
-}  // namespace spg
-extern "C" void spg_set_reverse(int reversed) { spg::g_reverse.store(reversed ? 1 : 0, std::memory_order_relaxed); }
-
-extern "C" void spg_set_pdl(int on) { spg::g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 extern "C" long long spg_launch_count(void) { return spg::g_launches.load(std::memory_order_relaxed); }
 extern "C" void spg_launch_count_reset(void) { spg::g_launches.store(0, std::memory_order_relaxed); }

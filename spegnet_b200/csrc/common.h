@@ -63,7 +63,26 @@ int make_tmap_qkv_window(CUtensorMap* out, const void* base, uint64_t B, uint64_
 int make_tmap_qkv_5d(CUtensorMap* out, const void* base, uint64_t BH, uint64_t W, uint64_t heads, uint32_t box_d,
                      uint32_t box_w, uint32_t box_h, int swizzle_bytes);
 
-int sm_count();
+int sm_count();  // of the CURRENT device (cached per device)
+
+// One-time-per-DEVICE guard for state that lives in a CUDA context (cudaFuncSetAttribute, __constant__ uploads): a
+// process that drives several GPUs must repeat it on each of them.  `if (once.needed()) { ...; once.done(); }`
+struct PerDeviceOnce {
+    unsigned long long mask[2] = {0, 0};  // up to 128 devices; benign race (the guarded work is idempotent)
+    static int device() {
+        int d = 0;
+        cudaGetDevice(&d);
+        return d & 127;
+    }
+    bool needed() const {
+        const int d = device();
+        return ((mask[d >> 6] >> (d & 63)) & 1ull) == 0;
+    }
+    void done() {
+        const int d = device();
+        mask[d >> 6] |= 1ull << (d & 63);
+    }
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL).  Every kernel of the library is launched with
@@ -74,15 +93,29 @@ int sm_count();
 // placed after the part of the prologue that touches no global data (barrier init, TMEM allocation, tensor-map
 // prefetch).  All global reads AND writes of a kernel come after its wait, so the stream's dependency semantics are
 // unchanged (no RAW / WAR hazard); what is hidden is the launch latency, the prologue and the tail of the previous
-// kernel -- 371 serialised launches per forward.  SPG_PDL=0 turns the attribute off (the instructions are then no-ops).
+// kernel -- 371 serialised launches per forward.  Requested per call (SPG_LAUNCH_PDL); without the attribute the
+// instructions are no-ops.
 // ---------------------------------------------------------------------------------------------------------------
-bool pdl_enabled();
+// SPG_PDL=0|1 in the environment pins the switch for every launch (debugging); -1 = not pinned.
+int pdl_pinned();
 
-// Traversal direction of the NEXT launch (spg_set_reverse): consecutive kernels of the forward are producer ->
-// consumer pairs over tensors larger than the 126 MB L2, so a consumer that walks its rows in the OPPOSITE order of
-// its producer starts on the lines that are still resident.  The GEMM / conv engine, LayerNorm and the attention
-// kernels honour the flag (tile / block / item index i -> n-1-i); the host flips it before every launch.
-bool traversal_reversed();
+// Per-call launch state decoded from the C-ABI descriptor (spg_launch_t): stream, programmatic dependent launch,
+// traversal direction.  Nothing here is process-global.
+//
+// Traversal direction: consecutive kernels of the forward are producer -> consumer pairs over tensors larger than the
+// 126 MB L2, so a consumer that walks its rows in the OPPOSITE order of its producer starts on the lines that are
+// still resident.  The GEMM / conv engine, LayerNorm and the attention kernels honour the flag (tile / block / item
+// index i -> n-1-i); the host alternates it launch by launch.
+struct LaunchCtx {
+    cudaStream_t stream;
+    bool pdl;
+    bool reverse;
+    explicit LaunchCtx(const spg_launch_t* l)
+        : stream(l != nullptr ? static_cast<cudaStream_t>(l->stream) : nullptr),
+          pdl(pdl_pinned() >= 0 ? pdl_pinned() != 0 : (l != nullptr && (l->flags & SPG_LAUNCH_PDL) != 0)),
+          reverse(l != nullptr && (l->flags & SPG_LAUNCH_REVERSE) != 0) {}
+    operator cudaStream_t() const { return stream; }
+};
 
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -93,17 +126,17 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, const LaunchCtx& st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
+    cfg.stream = st.stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = st.pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -737,10 +737,10 @@ struct EpiMaps {
     CUtensorMap out, res, ln;
 };
 
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, GemmArgs& a, const LaunchCtx& ctx) {
     const int total_1cta = a.num_m_tiles * a.num_n_tiles;
     const bool pair = a.pair != 0;
-    a.reverse = traversal_reversed() ? 1 : 0;
+    a.reverse = ctx.reverse ? 1 : 0;
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
     const int stage_bytes = a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128;
     const int staging = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
@@ -765,7 +765,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(64 + 32 * a.epi_warps);
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
+    cfg.stream = ctx.stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = pair ? 2 : 1;
@@ -774,35 +774,35 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em, Gemm
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see common.h "Programmatic dependent launch"
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = ctx.pdl ? 2 : 1;
     // the combinations SPEGNet launches get a compile-time specialised epilogue; anything else runs the generic one
 #define SPG_LAUNCH_ONE(ACT, F32, RES, HEAD, OUT, PAIR, EW)                                                         \
     do {                                                                                                           \
         auto kern = gemm_tcgen05_kernel<ACT, F32, RES, HEAD, OUT, PAIR, EW>;                                       \
-        static bool attr_set = false;                                                                              \
-        if (!attr_set) {                                                                                           \
+        static PerDeviceOnce attr_set;                                                                              \
+        if (attr_set.needed()) {                                                                                           \
             SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
-            attr_set = true;                                                                                       \
+            attr_set.done();                                                                                       \
         }                                                                                                          \
         SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, em.ln, a));                                 \
     } while (0)
 #define SPG_LAUNCH_ONE_UP2(PAIR)                                                                                   \
     do {                                                                                                           \
         auto kern = gemm_tcgen05_kernel<SPG_ACT_RELU, 0, 0, 0, 1, PAIR, kEpiWarpsDefault, 1>;                       \
-        static bool attr_set = false;                                                                              \
-        if (!attr_set) {                                                                                           \
+        static PerDeviceOnce attr_set;                                                                              \
+        if (attr_set.needed()) {                                                                                           \
             SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
-            attr_set = true;                                                                                       \
+            attr_set.done();                                                                                       \
         }                                                                                                          \
         SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, em.ln, a));                                 \
     } while (0)
 #define SPG_LAUNCH_ONE_LN(ACT, F32, RES, PAIR, LN)                                                                 \
     do {                                                                                                           \
         auto kern = gemm_tcgen05_kernel<ACT, F32, RES, 0, 1, PAIR, kEpiWarpsDefault, 0, LN>;                        \
-        static bool attr_set = false;                                                                              \
-        if (!attr_set) {                                                                                           \
+        static PerDeviceOnce attr_set;                                                                              \
+        if (attr_set.needed()) {                                                                                           \
             SPG_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));  \
-            attr_set = true;                                                                                       \
+            attr_set.done();                                                                                       \
         }                                                                                                          \
         SPG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, em.out, em.res, em.ln, a));                          \
     } while (0)
@@ -920,7 +920,7 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
 }  // namespace spg
 
 extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
-                              const spg_epilogue_t* ep, spg_stream_t stream) {
+                              const spg_epilogue_t* ep, const spg_launch_t* launch) {
     using namespace spg;
     SPG_CHECK_ARG(A != nullptr && W != nullptr, "A / W is NULL");
     SPG_CHECK_ARG(M > 0 && N > 0 && K > 0, "bad GEMM shape M=%d N=%d K=%d", M, N, K);
@@ -948,11 +948,11 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     CUtensorMap ta, tb;
     if (int rc = make_tmap_2d(&ta, A, M, K, static_cast<uint64_t>(K) * 2, kBlockM)) return rc;
     if (int rc = make_tmap_2d(&tb, W, N, K, static_cast<uint64_t>(K) * 2, a.pair ? a.block_n / 2 : a.block_n)) return rc;
-    return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
+    return launch_gemm(ta, tb, em, a, LaunchCtx(launch));
 }
 
 extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, int Cout,
-                               const spg_epilogue_t* ep, spg_stream_t stream) {
+                               const spg_epilogue_t* ep, const spg_launch_t* launch) {
     using namespace spg;
     SPG_CHECK_ARG(x != nullptr && w != nullptr, "x / w is NULL");
     SPG_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad conv shape B=%d H=%d W=%d", B, H, W);
@@ -986,11 +986,11 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     CUtensorMap ta, tb;
     if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, tile_h, a.halo ? 130 : tile_w)) return rc;
     if (int rc = make_tmap_2d(&tb, w, Cout, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;
-    return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
+    return launch_gemm(ta, tb, em, a, LaunchCtx(launch));
 }
 
 extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const float* corr, int B, int H, int W, int Cin,
-                                   int Cout, const float* bias4, void* out, spg_stream_t stream) {
+                                   int Cout, const float* bias4, void* out, const spg_launch_t* launch) {
     using namespace spg;
     SPG_CHECK_ARG(x != nullptr && w_phase != nullptr && corr != nullptr && out != nullptr, "x / w_phase / corr / out is NULL");
     SPG_CHECK_ARG(B > 0 && H >= 2 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
@@ -1034,7 +1034,7 @@ extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const flo
     CUtensorMap ta, tb;
     if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, 1, kBlockM)) return rc;
     if (int rc = make_tmap_2d(&tb, w_phase, 3ull * a.N, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;
-    return launch(ta, tb, em, a, static_cast<cudaStream_t>(stream));
+    return launch_gemm(ta, tb, em, a, LaunchCtx(launch));
 }
 
 #ifdef SPG_TRACE

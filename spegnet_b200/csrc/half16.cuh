@@ -22,12 +22,15 @@ constexpr int kHalfIsFp16 = 0;
 #define SPG_MMA_TYPE "bf16"
 #endif
 
+// Every 16-bit store saturates to the largest finite value (F2FP.SATFINITE, same single instruction): an fp16
+// activation beyond 65504 clamps instead of becoming inf and then NaN in the next LayerNorm / softmax
+// (tests/test_gpu_ops.py::test_fp16_stores_saturate, tests/test_gpu_model.py::test_large_activations_stay_finite).
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     uint32_t r;
 #ifdef SPG_FP16
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
 #else
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
 #endif
     return r;
 }
@@ -54,10 +57,13 @@ __device__ __forceinline__ float h_to_float(h16 v) {
 #endif
 }
 __device__ __forceinline__ h16 float_to_h(float f) {
+    unsigned short r;
 #ifdef SPG_FP16
-    return __float2half_rn(f);
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(f));
+    return __ushort_as_half(r);
 #else
-    return __float2bfloat16(f);
+    asm("cvt.rn.satfinite.bf16.f32 %0, %1;" : "=h"(r) : "f"(f));
+    return __ushort_as_bfloat16(r);
 #endif
 }
 __device__ __forceinline__ uint32_t max_h2(uint32_t a, uint32_t b) {

@@ -144,11 +144,11 @@ extern "C" size_t spg_preprocess_workspace_bytes(int H, int W, int S) {
 }
 
 extern "C" int spg_preprocess_rgb_u8(const unsigned char* img, int H, int W, float* out, int S, const float* mean3,
-                                     const float* std3, void* workspace, size_t ws_bytes, spg_stream_t stream) {
+                                     const float* std3, void* workspace, size_t ws_bytes, const spg_launch_t* launch) {
     SPG_CHECK_ARG(img && out && mean3 && std3 && workspace, "null pointer");
     SPG_CHECK_ARG(H > 0 && W > 0 && S > 0, "bad image shape H=%d W=%d S=%d", H, W, S);
     SPG_CHECK_ARG(ws_bytes >= spg_preprocess_workspace_bytes(H, W, S), "workspace too small (%zu bytes)", ws_bytes);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LaunchCtx st(launch);
     float* tmp = static_cast<float*>(workspace);
     const float sx = static_cast<float>(W) / static_cast<float>(S), sy = static_cast<float>(H) / static_cast<float>(S);
     const long long n1 = static_cast<long long>(H) * S;
@@ -162,11 +162,11 @@ extern "C" int spg_preprocess_rgb_u8(const unsigned char* img, int H, int W, flo
 }
 
 extern "C" int spg_resize_bilinear_f32(const float* src, int B, int Hi, int Wi, float* dst, int Ho, int Wo,
-                                       int apply_sigmoid, spg_stream_t stream) {
+                                       int apply_sigmoid, const spg_launch_t* launch) {
     SPG_CHECK_ARG(src && dst, "null pointer");
     SPG_CHECK_ARG(B > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0, "bad shape");
     const long long n = static_cast<long long>(Ho) * Wo;
-    SPG_CHECK_CUDA((launch_pdl(resize_bilinear_kernel, dim3(static_cast<unsigned>((n + 255) / 256), B), 256, 0, static_cast<cudaStream_t>(stream), src, Hi, Wi, dst, Ho, Wo, apply_sigmoid)));
+    SPG_CHECK_CUDA((launch_pdl(resize_bilinear_kernel, dim3(static_cast<unsigned>((n + 255) / 256), B), 256, 0, LaunchCtx(launch), src, Hi, Wi, dst, Ho, Wo, apply_sigmoid)));
     SPG_LAUNCHED();
     return SPG_OK;
 }

@@ -505,8 +505,8 @@ __global__ void __launch_bounds__(256) sod_finalize_kernel(const unsigned* __res
 
 // matlab-style fspecial('gaussian', 7, 5), as oracle/sod_metrics.py::_gauss7
 int upload_gauss7(cudaStream_t st) {
-    static bool done = false;
-    if (done) return SPG_OK;
+    static PerDeviceOnce once;  // c_gauss7 lives in each device's context
+    if (!once.needed()) return SPG_OK;
     double k[49], mx = 0.0, sum = 0.0;
     for (int i = 0; i < 7; ++i)
         for (int j = 0; j < 7; ++j) {
@@ -521,7 +521,7 @@ int upload_gauss7(cudaStream_t st) {
     if (sum != 0.0)
         for (int i = 0; i < 49; ++i) k[i] /= sum;
     SPG_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_gauss7, k, sizeof(k), 0, cudaMemcpyHostToDevice, st));
-    done = true;
+    once.done();
     return SPG_OK;
 }
 
@@ -542,12 +542,12 @@ extern "C" size_t spg_sod_workspace_bytes(int B, int H, int W) {
 
 extern "C" int spg_sod_gt_prepare_u8(const unsigned char* gt, int B, int H, int W, int* nearest,
                                      unsigned long long* gt_stats, void* workspace, size_t ws_bytes,
-                                     spg_stream_t stream) {
+                                     const spg_launch_t* launch) {
     SPG_CHECK_ARG(gt && nearest && gt_stats && workspace, "null pointer");
     SPG_CHECK_ARG(B > 0 && H > 0 && W > 0 && H <= 32767 && W <= 32767, "bad ground-truth shape B=%d H=%d W=%d", B, H, W);
     SPG_CHECK_ARG(static_cast<long long>(H) * W < (1ll << 31), "image too large");
     SPG_CHECK_ARG(ws_bytes >= spg_sod_workspace_bytes(B, H, W), "workspace too small (%zu bytes)", ws_bytes);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LaunchCtx st(launch);
     const size_t hw = static_cast<size_t>(B) * H * W;
     short* colfeat = static_cast<short*>(workspace);
     short* stack = colfeat + hw;
@@ -564,13 +564,13 @@ extern "C" int spg_sod_gt_prepare_u8(const unsigned char* gt, int B, int H, int 
 
 extern "C" int spg_sod_scores_u8(const unsigned char* pred, const unsigned char* gt, const int* nearest,
                                  const unsigned long long* gt_stats, int B, int H, int W, double* scores,
-                                 void* workspace, size_t ws_bytes, spg_stream_t stream) {
+                                 void* workspace, size_t ws_bytes, const spg_launch_t* launch) {
     SPG_CHECK_ARG(pred && gt && nearest && gt_stats && scores && workspace, "null pointer");
     SPG_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(pred) & 15) == 0 && (reinterpret_cast<uintptr_t>(gt) & 15) == 0,
                   "pred / gt must be 16-byte aligned");
     SPG_CHECK_ARG(ws_bytes >= spg_sod_workspace_bytes(B, H, W), "workspace too small (%zu bytes)", ws_bytes);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LaunchCtx st(launch);
     if (int rc = upload_gauss7(st)) return rc;
     unsigned* hist = static_cast<unsigned*>(workspace);
     const size_t hist_bytes = static_cast<size_t>(B) * 8 * 256 * sizeof(unsigned);

@@ -593,10 +593,10 @@ inline unsigned capped_blocks(long long total) {
 using namespace spg;
 
 extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
-                                      float eps, spg_stream_t stream) {
+                                      float eps, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && gamma && beta && y, "null pointer");
     SPG_CHECK_ARG(M > 0 && C > 0 && C % 4 == 0 && C <= kLnMaxC, "LayerNorm needs C %% 4 == 0 and C <= 1152 (C=%d)", C);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LaunchCtx st(launch);
     uint16_t* yo = static_cast<uint16_t*>(y);
     // rows per warp so that one block (8 warps) streams roughly 64 KB+ and the grid stays far below the block-launch rate
     // small M (batch 1): fewer rows per warp so that the grid still covers the machine
@@ -607,52 +607,52 @@ extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const f
     if (C <= 256) {
         const int rpw = fit(8, 2);  // 8 * 2 rows per warp
         const int rows_per_block = 8 * rpw * 2;
-        SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<16, 4>, (M + rows_per_block - 1) / rows_per_block, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
+        SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<16, 4>, (M + rows_per_block - 1) / rows_per_block, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, st.reverse ? 1 : 0)));
     } else {
         // register footprint follows the row length (float4 per lane): 3 for C <= 384, 5 for C <= 640, else 9
         const int rpw = fit(4, 1);
         const int rows_per_block = 8 * rpw;
         const unsigned grid = (M + rows_per_block - 1) / rows_per_block;
         if (C <= 384)
-            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 3>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 3>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, st.reverse ? 1 : 0)));
         else if (C <= 640)
-            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 5>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 5>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, st.reverse ? 1 : 0)));
         else
-            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 9>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, traversal_reversed() ? 1 : 0)));
+            SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 9>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, st.reverse ? 1 : 0)));
     }
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
-extern "C" int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, spg_stream_t stream) {
+extern "C" int spg_patchify_7x7s4(const float* x, void* cols, int B, int S, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && cols, "null pointer");
     SPG_CHECK_ARG(B > 0 && S > 0 && S % 4 == 0, "bad image size S=%d", S);
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "x must be 16-byte aligned");
     const long long total = static_cast<long long>(B) * (S / 4) * (S / 4) * 21;
-    SPG_CHECK_CUDA((launch_pdl(patchify_kernel, capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), x, static_cast<uint4*>(cols), B, S)));
+    SPG_CHECK_CUDA((launch_pdl(patchify_kernel, capped_blocks(total), 256, 0, LaunchCtx(launch), x, static_cast<uint4*>(cols), B, S)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
-extern "C" int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W, int C, spg_stream_t stream) {
+extern "C" int spg_maxpool2x2_f32(const float* x, float* y, int B, int H, int W, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && y, "null pointer");
     SPG_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && C % 4 == 0, "maxpool needs even H, W and C %% 4 == 0");
     const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * (C / 4);
-    SPG_CHECK_CUDA((launch_pdl(maxpool_kernel, capped_blocks(total), 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), B, H, W, C / 4)));
+    SPG_CHECK_CUDA((launch_pdl(maxpool_kernel, capped_blocks(total), 256, 0, LaunchCtx(launch), reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), B, H, W, C / 4)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
-extern "C" int spg_cast_f32_h16(const float* x, void* y, long long n, spg_stream_t stream) {
+extern "C" int spg_cast_f32_h16(const float* x, void* y, long long n, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && y, "null pointer");
     SPG_CHECK_ARG(n > 0 && n % 8 == 0, "cast needs n %% 8 == 0");
-    SPG_CHECK_CUDA((launch_pdl(cast_kernel, capped_blocks(n / 8), 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(x), static_cast<uint4*>(y), n / 8)));
+    SPG_CHECK_CUDA((launch_pdl(cast_kernel, capped_blocks(n / 8), 256, 0, LaunchCtx(launch), reinterpret_cast<const float4*>(x), static_cast<uint4*>(y), n / 8)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
 extern "C" int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0, const void* src1, int h1, int w1,
-                                        int c1, void* out, int B, int Ho, int Wo, spg_stream_t stream) {
+                                        int c1, void* out, int B, int Ho, int Wo, const spg_launch_t* launch) {
     SPG_CHECK_ARG(src0 && out, "null pointer");
     SPG_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0 && c0 > 0 && c1 >= 0, "channel counts must be multiples of 8");
     SPG_CHECK_ARG(c1 == 0 || src1 != nullptr, "src1 is NULL but c1 > 0");
@@ -660,51 +660,51 @@ extern "C" int spg_upsample_concat_h16(const void* src0, int h0, int w0, int c0,
     SPG_CHECK_ARG(Ho % h0 == 0 && Ho / h0 >= 2 && Wo % w0 == 0 && Wo / w0 >= 2, "src0 must be upsampled by an integer factor >= 2");
     SPG_CHECK_ARG(c1 == 0 || (Ho % h1 == 0 && Ho / h1 >= 2 && Wo % w1 == 0 && Wo / w1 >= 2),
                   "src1 must be upsampled by an integer factor >= 2");
-    SPG_CHECK_CUDA((launch_pdl(upcat_kernel, dim3(Ho / 2, B), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(src0), h0, w0, c0 / 8, static_cast<const uint4*>(src1), h1, w1, c1 / 8,
+    SPG_CHECK_CUDA((launch_pdl(upcat_kernel, dim3(Ho / 2, B), 256, 0, LaunchCtx(launch), static_cast<const uint4*>(src0), h0, w0, c0 / 8, static_cast<const uint4*>(src1), h1, w1, c1 / 8,
         static_cast<uint4*>(out), Ho, Wo)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
 extern "C" int spg_fusion_combine(const float* g2, const float* g3, const float* g4, const float* bias, void* fused,
-                                  float* row_sums, int B, int Hs, int C, spg_stream_t stream) {
+                                  float* row_sums, int B, int Hs, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(g2 && g3 && g4 && bias && fused && row_sums, "null pointer");
     SPG_CHECK_ARG(Hs % 4 == 0 && C % 4 == 0, "fusion_combine needs Hs %% 4 == 0 and C %% 4 == 0");
-    SPG_CHECK_CUDA((launch_pdl(fusion_combine_kernel, dim3(Hs, B), 128, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(g2), reinterpret_cast<const float4*>(g3), reinterpret_cast<const float4*>(g4),
+    SPG_CHECK_CUDA((launch_pdl(fusion_combine_kernel, dim3(Hs, B), 128, 0, LaunchCtx(launch), reinterpret_cast<const float4*>(g2), reinterpret_cast<const float4*>(g3), reinterpret_cast<const float4*>(g4),
         reinterpret_cast<const float4*>(bias), static_cast<uint2*>(fused), reinterpret_cast<float4*>(row_sums), Hs, C / 4)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
-extern "C" int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C, spg_stream_t stream) {
+extern "C" int spg_row_sums_h16(const void* x, float* row_sums, int B, int H, int W, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && row_sums, "null pointer");
     SPG_CHECK_ARG(C % 4 == 0, "row_sums needs C %% 4 == 0");
-    SPG_CHECK_CUDA((launch_pdl(row_sums_kernel, dim3(H, B), 128, 0, static_cast<cudaStream_t>(stream), static_cast<const uint2*>(x), reinterpret_cast<float4*>(row_sums), H, W, C / 4)));
+    SPG_CHECK_CUDA((launch_pdl(row_sums_kernel, dim3(H, B), 128, 0, LaunchCtx(launch), static_cast<const uint2*>(x), reinterpret_cast<float4*>(row_sums), H, W, C / 4)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
 extern "C" int spg_pooled_mlp(const float* row_sums, int rows, int count, const float* W1, const float* b1, int R,
-                              const float* W2, float* out, int B, int C, spg_stream_t stream) {
+                              const float* W2, float* out, int B, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(row_sums && W1 && out, "null pointer");
     SPG_CHECK_ARG(rows > 0 && count > 0 && R > 0 && C > 0, "bad pooled_mlp shape");
-    SPG_CHECK_CUDA((launch_pdl(pooled_mlp_kernel, B, 512, (C + R) * sizeof(float), static_cast<cudaStream_t>(stream), row_sums, rows, 1.0f / count, W1, b1, R, W2, out, C)));
+    SPG_CHECK_CUDA((launch_pdl(pooled_mlp_kernel, B, 512, (C + R) * sizeof(float), LaunchCtx(launch), row_sums, rows, 1.0f / count, W1, b1, R, W2, out, C)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
-extern "C" int spg_scale_channels_h16(void* x, const float* gate, int B, int HW, int C, spg_stream_t stream) {
+extern "C" int spg_scale_channels_h16(void* x, const float* gate, int B, int HW, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && gate, "null pointer");
     SPG_CHECK_ARG(C % 8 == 0, "scale_channels needs C %% 8 == 0");
     const long long total = static_cast<long long>(B) * HW * (C / 8);
-    SPG_CHECK_CUDA((launch_pdl(scale_channels_kernel, blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<uint4*>(x), gate, total, HW, C / 8)));
+    SPG_CHECK_CUDA((launch_pdl(scale_channels_kernel, blocks_for(total), 256, 0, LaunchCtx(launch), static_cast<uint4*>(x), gate, total, HW, C / 8)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
 extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* dw_bias, const float* gvec,
                                   const float* wf, const float* wf_bias, void* y, int B, int H, int W,
-                                  const int* dilations, spg_stream_t stream) {
+                                  const int* dilations, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && dw && dw_bias && gvec && wf && wf_bias && y && dilations, "null pointer");
     AsppParams p{static_cast<const uint4*>(x), dw, dw_bias, gvec, wf, wf_bias, static_cast<uint4*>(y), B, H, W,
                  {dilations[0], dilations[1], dilations[2], dilations[3]}};
@@ -716,22 +716,22 @@ extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* d
     const int rows = (band_rows + 2 * dmax) < H ? (band_rows + 2 * dmax) : H;
     const size_t smem = static_cast<size_t>(rows) * W * sizeof(uint4);
     SPG_CHECK_ARG(smem <= 200 * 1024, "e-ASPP band does not fit shared memory (W=%d, dilation %d)", W, dmax);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        SPG_CHECK_CUDA(cudaFuncSetAttribute(aspp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        smem_set = smem;
+    static PerDeviceOnce attr_set;
+    if (attr_set.needed()) {
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(aspp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set.done();
     }
     SPG_CHECK_CUDA((launch_pdl(aspp_kernel, dim3((H + band_rows - 1) / band_rows, 16, B), kAsppThreads, smem,
-                               static_cast<cudaStream_t>(stream), p, band_rows)));
+                               LaunchCtx(launch), p, band_rows)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
 extern "C" int spg_mask_stats_u8(const float* logits, const unsigned char* gt, unsigned char* mask, unsigned* stats,
-                                 int B, int HW, int double_sigmoid, spg_stream_t stream) {
+                                 int B, int HW, int double_sigmoid, const spg_launch_t* launch) {
     SPG_CHECK_ARG(logits && gt && mask && stats, "null pointer");
     SPG_CHECK_ARG(B > 0 && HW > 0, "bad shape B=%d HW=%d", B, HW);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LaunchCtx st(launch);
     SPG_CHECK_CUDA(cudaMemsetAsync(stats, 0, static_cast<size_t>(B) * 8 * sizeof(unsigned), st));
     if (HW % 4 != 0 || (reinterpret_cast<uintptr_t>(logits) & 15) || (reinterpret_cast<uintptr_t>(gt) & 3) ||
         (reinterpret_cast<uintptr_t>(mask) & 3)) {
@@ -747,19 +747,19 @@ extern "C" int spg_mask_stats_u8(const float* logits, const unsigned char* gt, u
     return SPG_OK;
 }
 
-extern "C" int spg_up2_border_gather_h16(const void* x, void* out, int B, int H, int W, int C, spg_stream_t stream) {
+extern "C" int spg_up2_border_gather_h16(const void* x, void* out, int B, int H, int W, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && out, "null pointer");
     SPG_CHECK_ARG(B > 0 && H >= 2 && W >= 2 && C % 8 == 0, "bad shape B=%d H=%d W=%d C=%d", B, H, W, C);
     const long long total = 2ll * B * H * 9 * (C / 8);
-    SPG_CHECK_CUDA((launch_pdl(up2_border_gather_kernel, blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(x), static_cast<uint4*>(out), B, H, W, C / 8)));
+    SPG_CHECK_CUDA((launch_pdl(up2_border_gather_kernel, blocks_for(total), 256, 0, LaunchCtx(launch), static_cast<const uint4*>(x), static_cast<uint4*>(out), B, H, W, C / 8)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
 
-extern "C" int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, spg_stream_t stream) {
+extern "C" int spg_nhwc_h16_to_nchw_f32(const void* x, float* y, int B, int HW, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(x && y, "null pointer");
     const long long total = static_cast<long long>(B) * HW * C;
-    SPG_CHECK_CUDA((launch_pdl(nhwc_to_nchw_kernel, blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream), static_cast<const uint16_t*>(x), y, HW, C, total)));
+    SPG_CHECK_CUDA((launch_pdl(nhwc_to_nchw_kernel, blocks_for(total), 256, 0, LaunchCtx(launch), static_cast<const uint16_t*>(x), y, HW, C, total)));
     SPG_LAUNCHED();
     return SPG_OK;
 }

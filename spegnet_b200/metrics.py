@@ -20,9 +20,15 @@ AGG_KEYS = ("s_alpha", "weighted_f", "mae", "e_phi", "mean_f")              # ut
 
 
 def quantise_gt(gt: torch.Tensor) -> torch.Tensor:
-    """``(g * 255).byte()`` of utils/metrics.py:220 for {0,1} masks; uint8 masks pass through."""
+    """``(g * 255).byte()`` of utils/metrics.py:220.  The reference applies it to every mask it is given ({0,1} floats
+    from CODImageProcessor.process_mask); a uint8 mask is taken as already quantised ({0,255}) unless its maximum is
+    <= 1, in which case it is the same {0,1} mask in integer form and is scaled like the reference would (no host
+    synchronisation: the scale factor is computed on the tensor's device)."""
     if gt.dtype == torch.uint8:
-        return gt.contiguous()
+        if gt.numel() == 0:
+            return gt.contiguous()
+        scale = (gt.max() <= 1).to(torch.uint8) * 254 + 1
+        return (gt * scale).contiguous()
     return (gt * 255).to(torch.uint8).contiguous()
 
 

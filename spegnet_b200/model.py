@@ -214,11 +214,23 @@ class SPEGNet(nn.Module):
         # traffic per batch-64 step, but measured 972 vs 981 img/s at batch 64 (the residual GEMMs pay for the second
         # store and the consumers for reading the row records) and 3.00 vs 3.09 ms at batch 1, and the row statistics
         # then depend on the n-tiling, i.e. on the batch size, in the last bit.  Off by default (SPG_LN_FUSE=1 enables).
-        self.ln_fuse = os.environ.get("SPG_LN_FUSE", "0") != "0"
         self._packed: Optional[Dict[str, torch.Tensor]] = None
+        self._ln_fuse = os.environ.get("SPG_LN_FUSE", "0") != "0"
         self._debug_taps: Optional[Dict[str, torch.Tensor]] = None  # tests: stream snapshot after every block
         self._workspaces: Dict[Tuple[int, int, str], _Workspace] = {}
         self.eval()
+
+    @property
+    def ln_fuse(self) -> bool:
+        return self._ln_fuse
+
+    @ln_fuse.setter
+    def ln_fuse(self, on: bool) -> None:
+        if bool(on) != self._ln_fuse:  # the folded weights W diag(gamma) are only packed when the switch is on
+            self._ln_fuse = bool(on)
+            self._packed = None
+            self._workspaces = {}
+            self._graphs = {}
 
     # ------------------------------------------------------------------ nn.Module protocol hooks
     def _apply(self, fn, *args, **kwargs):
@@ -245,13 +257,21 @@ class SPEGNet(nn.Module):
     # ------------------------------------------------------------------ one-time weight repack
     @torch.no_grad()
     def _pack(self) -> Dict[str, torch.Tensor]:
-        sd = {k: v for k, v in self.state_dict().items()}
+        """One-time weight repack: BatchNorm folding, [N,K] 16-bit Linear / tap-major conv layouts, per-scale split of
+        the fusion conv, the phase-folded stage-3 conv.  Runs on the HOST copy of the state dict (plain memcpys down
+        and up, no ATen kernels on the device): the first kernels a process launches on the GPU are the library's own."""
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("spegnet_b200.SPEGNet runs on a CUDA (B200) device only; call .to('cuda') first")
+        return {k: v.to(dev) for k, v in self._pack_host().items()}
+
+    @torch.no_grad()
+    def _pack_host(self) -> Dict[str, torch.Tensor]:
+        """The packed weights as host tensors (everything `_pack` uploads; also what the CPU tests inspect)."""
+        sd = {k: v.detach().to("cpu") for k, v in self.state_dict().items()}
         bf = self.compute_dtype
         W: Dict[str, torch.Tensor] = {}
-        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+        f32 = lambda t: t.to(torch.float32).contiguous()  # noqa: E731
         t = "encoder.encoder."
         # im2col column order of spg_patchify_7x7s4: k = (ky*3 + c)*8 + kx, slot kx = 7 zero -> K = 168
         pe = f32(sd[t + "patch_embed.proj.weight"]).permute(0, 2, 1, 3)  # [144, ky, c, kx]
@@ -272,7 +292,7 @@ class SPEGNet(nn.Module):
             # LayerNorm folded into its consumers: W' = W diag(gamma) (16 bit), column sums of the ROUNDED W' (they
             # multiply the row mean that the 16-bit operand still carries), bias' = b + W beta in fp32
             for c, n in (("qkv", "n1"), ("proj", "n1"), ("fc1", "n2")):
-                if dst + c + ".w" in W:
+                if self.ln_fuse and dst + c + ".w" in W:
                     wf = f32(sd[src + {"qkv": "attn.qkv", "proj": "proj", "fc1": "mlp.layers.0"}[c] + ".weight"])
                     wl = (wf * W[dst + n + ".w"][None, :]).to(bf).contiguous()
                     W[dst + c + ".wl"] = wl
@@ -343,14 +363,22 @@ class SPEGNet(nn.Module):
             W[f"head{i}.b"] = f32(sd[f"decoder.pred_heads.{i}.bias"])
         # scalar head biases as python floats (kernel arguments), read once here rather than per forward
         self._head_b = {k: float(W[k].item()) for k in ("edge.hb", "head0.b", "head1.b", "head2.b")}
+        if bf == torch.float16:
+            # fp16 storage: a folded weight beyond the fp16 range would become inf here (activations saturate in the
+            # kernels, half16.cuh); refuse it rather than produce NaN masks
+            for k, v in W.items():
+                if v.dtype == torch.float16 and not bool(torch.isfinite(v).all()):
+                    raise ValueError(f"packed weight {k!r} overflows fp16 (|w| > 65504): construct the model with "
+                                     "compute_dtype=torch.bfloat16 for this checkpoint")
+        self._pos_src = (W.pop("pos_embed"), W.pop("pos_embed_window"))  # host copies: interpolated per resolution
         return W
 
     def _pos_map(self, W: Dict[str, torch.Tensor], G: int) -> torch.Tensor:
         """bicubic(pos_embed 7x7 -> GxG) + tiled window embedding, [G*G, 144] fp32 (HF:modeling_sam2.py:623-629).
         Input independent: computed once per resolution at plan time, then fused as a residual of the
         patch-embedding GEMM."""
-        bg = F.interpolate(W["pos_embed"], size=(G, G), mode="bicubic")
-        win = W["pos_embed_window"]
+        pos, win = self._pos_src
+        bg = F.interpolate(pos, size=(G, G), mode="bicubic")
         tiled = win.repeat(1, 1, G // win.shape[-2], G // win.shape[-1])
         return (bg + tiled).permute(0, 2, 3, 1).reshape(G * G, -1).contiguous()
 
@@ -372,15 +400,16 @@ class SPEGNet(nn.Module):
         if self._packed is None:
             self._packed = self._pack()
         x = x.contiguous().float()
-        # programmatic dependent launch pays in the latency regime only (DESIGN.md "Measurement")
-        _lib.set_pdl(B <= max(self.cuda_graph_max_batch, 8))
-        if 0 < B <= self.cuda_graph_max_batch and self._debug_taps is None and not torch.cuda.is_current_stream_capturing():
-            return self._forward_graphed(x, B, S)
-        return self._forward_eager(x, B, S)
+        with torch.cuda.device(x.device):  # kernels, their attributes and the stream belong to the input's device
+            # programmatic dependent launch pays in the latency regime only (DESIGN.md "Measurement"); per-call flag
+            ops.set_pdl(B <= max(self.cuda_graph_max_batch, 8))
+            if 0 < B <= self.cuda_graph_max_batch and self._debug_taps is None and not torch.cuda.is_current_stream_capturing():
+                return self._forward_graphed(x, B, S)
+            return self._forward_eager(x, B, S)
 
     def _new_workspace(self, x: torch.Tensor, B: int, S: int) -> _Workspace:
         ws = _Workspace(B, S, x.device, self.spec, self.compute_dtype, ln_records=self.ln_fuse)
-        ws.pos = self._pos_map(self._packed, S // 4)
+        ws.pos = self._pos_map(self._packed, S // 4).to(x.device)
         return ws
 
     def _forward_eager(self, x: torch.Tensor, B: int, S: int, ws: Optional[_Workspace] = None) -> Dict[str, object]:

@@ -6,6 +6,8 @@ current CUDA stream.  No arithmetic happens in Python or in PyTorch ops here.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import threading
 from typing import Optional
 
 import torch
@@ -15,17 +17,55 @@ from ._lib import ACT_GELU, ACT_NONE, ACT_RELU, F32, Epilogue  # noqa: F401
 from ._lib import H16 as OUT_H16
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+class _LaunchState(threading.local):
+    """Host-side launch policy of the calling thread; handed to the library per call (spg_launch_t), never stored in it."""
+
+    pdl = False      # programmatic dependent launch: pays in the latency regime (small batches), see SPEGNet.forward
+    direction = 0    # traversal direction of the next direction-aware launch (alternates: DESIGN.md "Launch structure")
+
+
+_state = _LaunchState()
+_SNAKE = os.environ.get("SPG_SNAKE", "1") != "0"
+
+
+def set_pdl(on: bool) -> None:
+    """Request programmatic dependent launch for the calls this thread makes from now on (SPG_LAUNCH_PDL)."""
+    _state.pdl = bool(on)
+
+
+def _launch(flip: bool = False):
+    """spg_launch_t for the next call: torch's current stream + this thread's flags.  `flip` alternates the traversal
+    direction (GEMM / conv / LayerNorm / attention): each consumer starts on the rows its producer wrote last."""
+    flags = _lib.LAUNCH_PDL if _state.pdl else 0
+    if flip and _SNAKE:
+        _state.direction ^= 1
+    if flip and _state.direction:
+        flags |= _lib.LAUNCH_REVERSE
+    return C.byref(_lib.Launch(torch.cuda.current_stream().cuda_stream, flags))
 
 
 H16 = "h16"  # marker: a 16-bit operand (fp16 or bf16; selects the library variant)
 
 
+def _on_current_device(t: torch.Tensor) -> None:
+    """Kernels, their per-device attributes and the stream all belong to the CURRENT CUDA device: an operand that lives
+    on another GPU is an error, not something to launch on (wrap the call in `torch.cuda.device(t.device)`)."""
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise ValueError(f"operand is on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                         "call under `with torch.cuda.device(tensor.device):`")
+
+
 def _lib_for(t: torch.Tensor):
     """(library, dtype name) for the 16-bit operand `t`."""
+    _on_current_device(t)
     name = _lib.dtype_name(t.dtype)
     return _lib.load(name), name
+
+
+def _default_lib(t: torch.Tensor):
+    """(library, dtype name) for the entry points without a 16-bit operand (either variant serves them)."""
+    _on_current_device(t)
+    return _lib.load(), _lib.DEFAULT_DTYPE
 
 
 def _ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optional[int]:
@@ -82,9 +122,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bia
         raise ValueError(f"weight K {w.shape[1]} != activation K {K}")
     ep = _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_fold, ln_emit)
     lib, dn = _lib_for(a)
-    _lib.flip_direction()
     rc = lib.spg_linear_h16(_ptr(a, H16, "a"), _ptr(w, H16, "w"), M, N, K,
-                                     C.byref(ep), _stream())
+                                     C.byref(ep), _launch(True))
     _lib.check(rc, "spg_linear_h16", dn)
 
 
@@ -97,9 +136,8 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bi
         raise ValueError("conv weight must be [Cout, 9*Cin]")
     ep = _epilogue(out, bias, act, None, 0, head_w, head_b, head_out)
     lib, dn = _lib_for(x)
-    _lib.flip_direction()
     rc = lib.spg_conv3x3_h16(_ptr(x, H16, "x"), _ptr(w, H16, "w"), B, H, W, Cin, Cout,
-                                      C.byref(ep), _stream())
+                                      C.byref(ep), _launch(True))
     _lib.check(rc, "spg_conv3x3_h16", dn)
 
 
@@ -109,7 +147,7 @@ def up2_border_gather(x: torch.Tensor, out: torch.Tensor) -> None:
     if tuple(out.shape) != (2, B * H, 9 * Cc):
         raise ValueError(f"out must be [2, {B * H}, {9 * Cc}], got {tuple(out.shape)}")
     lib, dn = _lib_for(x)
-    rc = lib.spg_up2_border_gather_h16(_ptr(x, H16, "x"), _ptr(out, H16, "out"), B, H, W, Cc, _stream())
+    rc = lib.spg_up2_border_gather_h16(_ptr(x, H16, "x"), _ptr(out, H16, "out"), B, H, W, Cc, _launch())
     _lib.check(rc, "spg_up2_border_gather_h16", dn)
 
 
@@ -123,47 +161,44 @@ def conv3x3_up2(x: torch.Tensor, w_phase: torch.Tensor, corr: torch.Tensor, bias
     if tuple(out.shape) != (B, 2 * H, 2 * W, Cout) or tuple(corr.shape) != (2, B * H, 4 * Cout):
         raise ValueError("out / corr shape does not match x and w_phase")
     lib, dn = _lib_for(x)
-    _lib.flip_direction()
     rc = lib.spg_conv3x3_up2_h16(_ptr(x, H16, "x"), _ptr(w_phase, H16, "w_phase"), _ptr(corr, torch.float32, "corr"),
-                                 B, H, W, Cin, Cout, _ptr(bias4, torch.float32, "bias4"), _ptr(out, H16, "out"), _stream())
+                                 B, H, W, Cin, Cout, _ptr(bias4, torch.float32, "bias4"), _ptr(out, H16, "out"), _launch(True))
     _lib.check(rc, "spg_conv3x3_up2_h16", dn)
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, eps: float) -> None:
     M, Cc = x.shape
     lib, dn = _lib_for(y)
-    _lib.flip_direction()
     rc = lib.spg_layernorm_f32_h16(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
                                             _ptr(beta, torch.float32, "beta"), _ptr(y, H16, "y"), M, Cc,
-                                            eps, _stream())
+                                            eps, _launch(True))
     _lib.check(rc, "spg_layernorm_f32_h16", dn)
 
 
 def patchify(x: torch.Tensor, cols: torch.Tensor) -> None:
     B, _, S, _ = x.shape
     lib, dn = _lib_for(cols)
-    rc = lib.spg_patchify_7x7s4(_ptr(x, torch.float32, "x"), _ptr(cols, H16, "cols"), B, S, _stream())
+    rc = lib.spg_patchify_7x7s4(_ptr(x, torch.float32, "x"), _ptr(cols, H16, "cols"), B, S, _launch())
     _lib.check(rc, "spg_patchify_7x7s4", dn)
 
 
 def maxpool2x2(x: torch.Tensor, y: torch.Tensor, B: int, H: int, W: int, Cc: int) -> None:
-    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
-    rc = lib.spg_maxpool2x2_f32(_ptr(x, torch.float32, "x"), _ptr(y, torch.float32, "y"), B, H, W, Cc, _stream())
+    lib, dn = _default_lib(x)
+    rc = lib.spg_maxpool2x2_f32(_ptr(x, torch.float32, "x"), _ptr(y, torch.float32, "y"), B, H, W, Cc, _launch())
     _lib.check(rc, "spg_maxpool2x2_f32", dn)
 
 
 def cast_h16(x: torch.Tensor, y: torch.Tensor) -> None:
     lib, dn = _lib_for(y)
-    rc = lib.spg_cast_f32_h16(_ptr(x, torch.float32, "x"), _ptr(y, H16, "y"), x.numel(), _stream())
+    rc = lib.spg_cast_f32_h16(_ptr(x, torch.float32, "x"), _ptr(y, H16, "y"), x.numel(), _launch())
     _lib.check(rc, "spg_cast_f32_h16", dn)
 
 
 def window_attention(qkv: torch.Tensor, out: torch.Tensor, B: int, H: int, W: int, D: int, heads: int, window: int,
                      q_pool: bool) -> None:
     lib, dn = _lib_for(qkv)
-    _lib.flip_direction()
     rc = lib.spg_window_attention_h16(_ptr(qkv, H16, "qkv"), _ptr(out, H16, "out"), B,
-                                               H, W, D, heads, window, int(q_pool), _stream())
+                                               H, W, D, heads, window, int(q_pool), _launch(True))
     _lib.check(rc, "spg_window_attention_h16", dn)
 
 
@@ -172,9 +207,8 @@ def window_attention_tc(qkv: torch.Tensor, out: torch.Tensor, B: int, H: int, W:
     """The tcgen05 / TMEM attention kernels directly (16x16 windows or global, no query pooling); `window_attention`
     dispatches to them whenever they apply.  See spg_window_attention_tc_h16."""
     lib, dn = _lib_for(qkv)
-    _lib.flip_direction()
     rc = lib.spg_window_attention_tc_h16(_ptr(qkv, H16, "qkv"), _ptr(out, H16, "out"), B, H, W, D, heads, window,
-                                         int(q_pool), _stream())
+                                         int(q_pool), _launch(True))
     _lib.check(rc, "spg_window_attention_tc_h16", dn)
 
 
@@ -187,7 +221,7 @@ def upsample_concat(src0: torch.Tensor, src1: Optional[torch.Tensor], out: torch
     lib, dn = _lib_for(src0)
     rc = lib.spg_upsample_concat_h16(_ptr(src0, H16, "src0"), h0, w0, c0,
                                               _ptr(src1, H16, "src1"), h1, w1, c1,
-                                              _ptr(out, H16, "out"), B, Ho, Wo, _stream())
+                                              _ptr(out, H16, "out"), B, Ho, Wo, _launch())
     _lib.check(rc, "spg_upsample_concat_h16", dn)
 
 
@@ -196,29 +230,29 @@ def fusion_combine(g2, g3, g4, bias, fused, row_sums, B: int, Hs: int, Cc: int) 
     rc = lib.spg_fusion_combine(_ptr(g2, torch.float32, "g2"), _ptr(g3, torch.float32, "g3"),
                                         _ptr(g4, torch.float32, "g4"), _ptr(bias, torch.float32, "bias"),
                                         _ptr(fused, H16, "fused"), _ptr(row_sums, torch.float32, "row_sums"),
-                                        B, Hs, Cc, _stream())
+                                        B, Hs, Cc, _launch())
     _lib.check(rc, "spg_fusion_combine", dn)
 
 
 def row_sums(x, out, B: int, H: int, W: int, Cc: int) -> None:
     lib, dn = _lib_for(x)
     rc = lib.spg_row_sums_h16(_ptr(x, H16, "x"), _ptr(out, torch.float32, "row_sums"), B, H, W, Cc,
-                                       _stream())
+                                       _launch())
     _lib.check(rc, "spg_row_sums_h16", dn)
 
 
 def pooled_mlp(row_sums_t, rows: int, count: int, w1, b1, R: int, w2, out, B: int, Cc: int) -> None:
-    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    lib, dn = _default_lib(row_sums_t)
     rc = lib.spg_pooled_mlp(_ptr(row_sums_t, torch.float32, "row_sums"), rows, count,
                                     _ptr(w1, torch.float32, "w1"), _ptr(b1, torch.float32, "b1"), R,
-                                    _ptr(w2, torch.float32, "w2"), _ptr(out, torch.float32, "out"), B, Cc, _stream())
+                                    _ptr(w2, torch.float32, "w2"), _ptr(out, torch.float32, "out"), B, Cc, _launch())
     _lib.check(rc, "spg_pooled_mlp", dn)
 
 
 def scale_channels(x, gate, B: int, HW: int, Cc: int) -> None:
     lib, dn = _lib_for(x)
     rc = lib.spg_scale_channels_h16(_ptr(x, H16, "x"), _ptr(gate, torch.float32, "gate"), B, HW, Cc,
-                                             _stream())
+                                             _launch())
     _lib.check(rc, "spg_scale_channels_h16", dn)
 
 
@@ -228,14 +262,14 @@ def easpp_branches(x, dw, dw_bias, gvec, wf, wf_bias, y, B: int, H: int, W: int,
     rc = lib.spg_easpp_branches(_ptr(x, H16, "x"), _ptr(dw, torch.float32, "dw"),
                                         _ptr(dw_bias, torch.float32, "dw_bias"), _ptr(gvec, torch.float32, "gvec"),
                                         _ptr(wf, torch.float32, "wf"), _ptr(wf_bias, torch.float32, "wf_bias"),
-                                        _ptr(y, H16, "y"), B, H, W, dil, _stream())
+                                        _ptr(y, H16, "y"), B, H, W, dil, _launch())
     _lib.check(rc, "spg_easpp_branches", dn)
 
 
 def nhwc_to_nchw_f32(x: torch.Tensor, y: torch.Tensor, B: int, HW: int, Cc: int) -> None:
     lib, dn = _lib_for(x)
     rc = lib.spg_nhwc_h16_to_nchw_f32(_ptr(x, H16, "x"), _ptr(y, torch.float32, "y"), B, HW, Cc,
-                                               _stream())
+                                               _launch())
     _lib.check(rc, "spg_nhwc_h16_to_nchw_f32", dn)
 
 
@@ -246,10 +280,10 @@ def mask_stats(logits: torch.Tensor, gt_u8: torch.Tensor, double_sigmoid: bool =
     HW = logits[0].numel()
     mask = torch.empty(B, *gt_u8.shape[1:], dtype=torch.uint8, device=logits.device)
     stats = torch.empty(B, 8, dtype=torch.int32, device=logits.device)
-    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    lib, dn = _default_lib(logits)
     rc = lib.spg_mask_stats_u8(_ptr(logits, torch.float32, "logits"), _ptr(gt_u8, torch.uint8, "gt"),
                                _ptr(mask, torch.uint8, "mask"), _ptr(stats, torch.int32, "stats"), B, HW,
-                               int(double_sigmoid), _stream())
+                               int(double_sigmoid), _launch())
     _lib.check(rc, "spg_mask_stats_u8", dn)
     return mask, stats[:, :5].to(torch.int64)
 
@@ -270,14 +304,14 @@ def sod_gt_prepare(gt_u8: torch.Tensor):
     """gt_u8 [B,H,W] uint8 (foreground > 128) -> (nearest int32 [B,H,W], gt_stats int64 [B,4]).  Ground truth only:
     cache the result per dataset.  See spg_sod_gt_prepare_u8."""
     B, H, W = gt_u8.shape
-    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    lib, dn = _default_lib(gt_u8)
     nbytes = int(lib.spg_sod_workspace_bytes(B, H, W))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=gt_u8.device)
     nearest = torch.empty(B, H, W, dtype=torch.int32, device=gt_u8.device)
     stats = torch.empty(B, 4, dtype=torch.int64, device=gt_u8.device)
     rc = lib.spg_sod_gt_prepare_u8(_ptr(gt_u8, torch.uint8, "gt"), B, H, W, _ptr(nearest, torch.int32, "nearest"),
                                    _ptr(stats, torch.int64, "gt_stats"), _ptr(ws, torch.uint8, "workspace"), nbytes,
-                                   _stream())
+                                   _launch())
     _lib.check(rc, "spg_sod_gt_prepare_u8", dn)
     return nearest, stats
 
@@ -288,14 +322,14 @@ def sod_scores(pred_u8: torch.Tensor, gt_u8: torch.Tensor, nearest: torch.Tensor
     B, H, W = gt_u8.shape
     if tuple(pred_u8.shape) != (B, H, W):
         raise ValueError(f"pred {tuple(pred_u8.shape)} and gt {tuple(gt_u8.shape)} differ")
-    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    lib, dn = _default_lib(pred_u8)
     nbytes = int(lib.spg_sod_workspace_bytes(B, H, W))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=gt_u8.device)
     scores = torch.empty(B, 5, dtype=torch.float64, device=gt_u8.device)
     rc = lib.spg_sod_scores_u8(_ptr(pred_u8, torch.uint8, "pred"), _ptr(gt_u8, torch.uint8, "gt"),
                                _ptr(nearest, torch.int32, "nearest"), _ptr(gt_stats, torch.int64, "gt_stats"), B, H, W,
                                _ptr(scores, torch.float64, "scores"), _ptr(ws, torch.uint8, "workspace"), nbytes,
-                               _stream())
+                               _launch())
     _lib.check(rc, "spg_sod_scores_u8", dn)
     return scores
 
@@ -312,7 +346,7 @@ def preprocess_rgb(img_u8: torch.Tensor, size: int, mean=IMAGENET_MEAN, std=IMAG
     if img_u8.dim() != 3 or img_u8.shape[2] != 3:
         raise ValueError(f"expected a uint8 [H,W,3] image, got {tuple(img_u8.shape)}")
     H, W, _ = img_u8.shape
-    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    lib, dn = _default_lib(img_u8)
     if out is None:
         out = torch.empty(3, size, size, dtype=torch.float32, device=img_u8.device)
     nbytes = int(lib.spg_preprocess_workspace_bytes(H, W, size))
@@ -320,7 +354,7 @@ def preprocess_rgb(img_u8: torch.Tensor, size: int, mean=IMAGENET_MEAN, std=IMAG
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
     rc = lib.spg_preprocess_rgb_u8(_ptr(img_u8, torch.uint8, "img"), H, W, _ptr(out, torch.float32, "out"), size, m, s,
-                                   _ptr(ws, torch.uint8, "workspace"), nbytes, _stream())
+                                   _ptr(ws, torch.uint8, "workspace"), nbytes, _launch())
     _lib.check(rc, "spg_preprocess_rgb_u8", dn)
     return out
 
@@ -335,8 +369,8 @@ def resize_bilinear(src: torch.Tensor, size, sigmoid: bool = False) -> torch.Ten
     for d in lead:
         B *= int(d)
     dst = torch.empty(*lead, ho, wo, dtype=torch.float32, device=src.device)
-    lib, dn = _lib.load(), _lib.DEFAULT_DTYPE
+    lib, dn = _default_lib(src)
     rc = lib.spg_resize_bilinear_f32(_ptr(src, torch.float32, "src"), B, hi, wi, _ptr(dst, torch.float32, "dst"), ho, wo,
-                                     int(sigmoid), _stream())
+                                     int(sigmoid), _launch())
     _lib.check(rc, "spg_resize_bilinear_f32", dn)
     return dst

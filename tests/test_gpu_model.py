@@ -228,6 +228,26 @@ def test_host_pipeline_returns_the_forward_results_in_order(spread_sd):
         assert torch.equal(gp, wp) and torch.equal(ge, we)
 
 
+def test_host_pipeline_depth3_ragged_after_unsynchronised_warmup(model_fp16):
+    """Ring of three buffers, batch shapes that change (ragged last batches) and a warm-up forward that is still
+    running when the first copy is issued: the freshly allocated input buffers must not be written by the copy stream
+    before the compute stream is done with the memory they came from."""
+    from spegnet_b200 import HostPipeline
+
+    g = torch.Generator().manual_seed(33)
+    batches = [torch.randn(b, 3, 256, 256, generator=g).pin_memory() for b in (3, 3, 2, 3, 1, 2)]
+    want = []
+    with torch.no_grad():
+        for x in batches:
+            out = model_fp16(x.cuda())
+            want.append((out["predictions"][-1].cpu(), out["edge"].cpu()))
+        model_fp16(torch.randn(16, 3, 256, 256, generator=g).cuda())  # no synchronise: kernels still queued
+    got = [(o["prediction"].clone(), o["edge"].clone()) for o in HostPipeline(model_fp16, depth=3).run(batches)]
+    assert len(got) == len(want)
+    for (gp, ge), (wp, we) in zip(got, want):
+        assert torch.equal(gp, wp) and torch.equal(ge, we)
+
+
 def test_layernorm_folded_trunk_keeps_mask_parity(spread_sd):
     """The opt-in trunk with every LayerNorm folded into its producer / consumer GEMMs (model.ln_fuse) against the
     fp32 oracle: same 1e-2 mask bar as the default path."""
