@@ -37,6 +37,13 @@ NCU_TRAFFIC = {"bytes_per_launch": 77_608_192 + 173_853_952, "launch": "stage-3 
                "algorithmic_bytes": 65536 * 576 * 2 + 1728 * 576 * 2 + 65536 * 1728 * 2,
                "source": "profiles/r01_gemm_qkv_ncu_full_summary.txt"}
 FALLBACK_PEAKS = {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
+# What each storage type is good for (DESIGN.md "Numerics", profiles/r02_precision_budget.md): masks vs the fp32
+# reference on the seed-0 spread fixture, max |delta sigmoid|; the north-star bar is 1e-2.
+PARITY_NOTE = {
+    "fp16": "parity build: max |d sigmoid| 7e-3 vs fp32 (bar 1e-2); eager torch fp16 autocast measures 1.3e-2, TF32 8.5e-3",
+    "bf16": "8-bit mantissa: max |d sigmoid| 4.7e-2 vs fp32 (bar 1e-2 not met); eager torch bf16 autocast measures 1.1e-1 "
+            "on the same fixture -- no bf16-operand pipeline meets the bar, this one is 2.3x closer than the library's",
+}
 CFG = {"encoder": {"config_path": "configs/sam2.1/sam2.1_hiera_l.yaml",
                    "checkpoint_path": "./checkpoints/sam2.1_hiera_large.pt", "variant": "large"}}
 
@@ -163,27 +170,13 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def run_dataset(args):
-    """--dataset N: BASELINE config 4 -- batch-sharded evaluation of an N-image synthetic set (COD10K-test size: 2026)
-    with the five scores computed on the GPU; one all_gather of [ceil(N/W), 6] fp64 rows per dataset."""
+def dataset_record(model, N: int, B: int, S: int, dev, dist, rank: int, world: int, dtype: str):
+    """BASELINE config 4: batch-sharded evaluation of an N-image synthetic set (COD10K-test size: 2026) with the five
+    scores computed on the GPU; one all_gather of [ceil(N/W), 6] fp64 rows per dataset.  Returns the record (rank 0)."""
     import torch
 
-    from spegnet_b200 import SPEGNet, _lib, evaluate, sharded
+    from spegnet_b200 import _lib, evaluate, sharded
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
-
-        dist = dist_mod
-        _init_nccl(dist, dev)
-    torch.manual_seed(0)
-    model = SPEGNet(CFG, compute_dtype=torch.float16 if args.dtype == "fp16" else torch.bfloat16).to(dev).eval()
-    N, B, S = args.dataset, args.batch, args.size
     mine = sharded.shard_indices(N, rank, world)
     gen = evaluate.synthetic_batch_fn(S, dev)
     # this rank's shard, resident in HBM before the timed region (inputs are synthetic; loading is out of scope)
@@ -213,17 +206,40 @@ def run_dataset(args):
             tmax = torch.tensor([ms], device=dev)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             ms = float(tmax.item())
+    scores = {k: round(float(result[k]), 6) for k in ("s_alpha", "weighted_f", "mae", "e_phi", "mean_f")}
+    return {
+        "metric": "images_per_sec", "value": round(N / (ms * 1e-3), 2), "unit": "images/s", "n_gpus": world,
+        "steps": 1, "warmup": 2, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": f"batch-sharded evaluation of a {N}-image synthetic set at {S}x{S} with on-GPU "
+                               "S-alpha / weighted F-beta / E-phi / MAE / mean F-beta (BASELINE config 4)",
+                   "batch_per_gpu": B, "size": S, "parallelism": f"batch-sharded x{world}",
+                   "collective": "one all_gather of [ceil(N/W), 6] fp64 rows"},
+        "scores": scores, "gpu_launches": int(_lib.launch_count())}
+
+
+def run_dataset(args):
+    """--dataset N: BASELINE config 4 as the whole run (the default run reports it under `extra_configs`)."""
+    import torch
+
+    from spegnet_b200 import SPEGNet
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        _init_nccl(dist, dev)
+    torch.manual_seed(0)
+    model = SPEGNet(CFG, compute_dtype=torch.float16 if args.dtype == "fp16" else torch.bfloat16).to(dev).eval()
+    rec = dataset_record(model, args.dataset, args.batch, args.size, dev, dist, rank, world, args.dtype)
     if rank == 0:
-        scores = {k: round(float(result[k]), 6) for k in ("s_alpha", "weighted_f", "mae", "e_phi", "mean_f")}
-        print(json.dumps({
-            "metric": "images_per_sec", "value": round(N / (ms * 1e-3), 2), "unit": "images/s", "n_gpus": world,
-            "steps": 1, "warmup": 2, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"batch-sharded evaluation of a {N}-image synthetic set at {S}x{S} with on-GPU "
-                                   "S-alpha / weighted F-beta / E-phi / MAE / mean F-beta (BASELINE config 4)",
-                       "batch_per_gpu": B, "size": S, "parallelism": f"batch-sharded x{world}",
-                       "collective": "one all_gather of [ceil(N/W), 6] fp64 rows"},
-            "scores": scores, "gpu_launches": int(_lib.launch_count())}), flush=True)
+        print(json.dumps(rec), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -251,68 +267,76 @@ def _init_nccl(dist, dev):
         dist.barrier()  # creates the communicator (and its banner) now, not inside the timed region
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE config 2: 64)")
-    ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--dtype", default=os.environ.get("SPEGNET_B200_DTYPE", "fp16"), choices=["fp16", "bf16"])
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of host CPU time for cpu_baseline")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-latency", action="store_true")
-    ap.add_argument("--dataset", type=int, default=0, help="evaluate an N-image synthetic set instead (BASELINE config 4)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    if args.dataset > 0:
-        return run_dataset(args)
-    if args.warmup < 3:
-        args.warmup = 3
-
+def gpu_library_rate(state_dict, B: int, S: int, dev, iters: int = 3):
+    """The "library call" bar: the reference's algorithm as eager PyTorch on THIS GPU --
+    the oracle port of SPEGNet.forward moved to cuda (cuBLAS / cuDNN / ATen kernels, the code path the reference's
+    nn.Modules dispatch to), fp32 with TF32 allowed and under bf16 autocast, CUDA-event timed.  A baseline leg like
+    cpu_baseline: the oracle is the thing timed here, never the product."""
     import torch
 
-    from spegnet_b200 import SPEGNet, _lib, ops
+    from oracle.spegnet import spegnet_forward
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: spegnet_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_mod
+    sd = {k: v.to(dev) for k, v in state_dict.items()}
+    x = torch.randn(B, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    out = {}
+    for name in ("fp32_tf32", "bf16_autocast"):
+        torch.backends.cuda.matmul.allow_tf32 = True
+        torch.backends.cudnn.allow_tf32 = True
 
-        dist = dist_mod
-        _init_nccl(dist, dev)
-    lib = _lib.load(args.dtype)
-    if lib.spg_device_check() != 0:
-        raise SystemExit(lib.spg_last_error().decode())
+        def fwd():
+            if name == "bf16_autocast":
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return spegnet_forward(sd, x)
+            return spegnet_forward(sd, x)
 
-    torch.manual_seed(0)  # identical random-init weights on every rank
-    model = SPEGNet(CFG, compute_dtype=torch.float16 if args.dtype == "fp16" else torch.bfloat16)
-    cpu_sd = {k: v.clone() for k, v in model.state_dict().items()} if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
-    model = model.to(dev).eval()
+        try:
+            fwd()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[name] = {"value": round(B / ms * 1e3, 2), "unit": "images/s", "ms_per_step": round(ms, 2)}
+        except RuntimeError as exc:  # e.g. out of memory on a shared box: report, do not fail the bench
+            out[name] = {"value": None, "error": str(exc).splitlines()[0][:200]}
+        torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out["what"] = (f"oracle port of SPEGNet.forward on cuda (eager torch {torch.__version__}: cuBLAS / cuDNN / ATen), "
+                   f"batch {B}, {S}x{S}, {iters} timed forwards, CUDA events")
+    return out
 
-    B, S = args.batch, args.size
+
+def measure(model, args, B: int, S: int, dev, dist, rank: int, world: int, steps: int, warmup: int, e2e_steps: int,
+            instrument: bool = True):
+    """Device-timed throughput (CUDA events, inputs resident in HBM) + host-to-host throughput of one model."""
+    import torch
+
+    from spegnet_b200 import _lib, ops
+    from spegnet_b200.pipeline import HostPipeline
+
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # three different resident batches, rotated, so that no step re-reads its predecessor's inputs; the
     # per-step activation working set (~13 GB at B=64) is two orders of magnitude beyond the 126 MB L2.
     batches = [torch.randn(B, 3, S, S, device=dev, generator=gen) for _ in range(3)]
-
     gt = (torch.rand(B, S, S, device=dev, generator=gen) > 0.75).to(torch.uint8) * 255  # synthetic ground truth
+    partials = []
 
     def step(i):
         out = model(batches[i % 3])
-        # per-image predictions -> uint8 masks + integer MAE partials on the GPU (utils/metrics.py:205-210), and the
-        # only collective of the path: one all_gather of 5 integers per image
-        _, stats = ops.mask_stats(out["predictions"][-1], gt, True)
+        # per-image predictions -> uint8 masks + integer MAE partials on the GPU (utils/metrics.py:205-210); the
+        # partials of all steps are exchanged by ONE all_gather at the end of the run (the only collective of the
+        # path, SURVEY.md 8(e)) -- no per-step rendezvous, every GPU runs at its own pace
+        partials.append(ops.mask_stats(out["predictions"][-1], gt, True)[1])
+
+    def gather_partials():
+        stats = torch.stack(partials)
+        partials.clear()
         if dist is not None:
-            gathered = torch.empty(world * B, stats.shape[1], dtype=stats.dtype, device=dev)
+            gathered = torch.empty(world, *stats.shape, dtype=stats.dtype, device=dev)
             dist.all_gather_into_tensor(gathered, stats)
             return gathered
         return stats
@@ -344,43 +368,49 @@ def main():
         # 4 phases x Cout outputs per low-resolution pixel over K = 9*Cin: the FLOPs of the 3x3 conv on the 2x grid
         gemm_events.append((e0, e1, 2.0 * x.shape[0] * x.shape[1] * x.shape[2] * (w_phase.shape[0] // 3) * w_phase.shape[1]))
 
+    res = {}
     with torch.no_grad():
-        for i in range(args.warmup):
+        for i in range(warmup):
             step(i)
+        gather_partials()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(torch.cuda.current_device())
         if rank == 0:
             sampler.start()
         _lib.reset_launch_count()
-        ops.linear, ops.conv3x3, ops.conv3x3_up2 = timed_linear, timed_conv, timed_conv_up2
+        if instrument:
+            ops.linear, ops.conv3x3, ops.conv3x3_up2 = timed_linear, timed_conv, timed_conv_up2
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         t0.record()
-        for i in range(args.steps):
+        for i in range(steps):
             step(i)
+        gather_partials()
         t1.record()
         torch.cuda.synchronize()
         ops.linear, ops.conv3x3, ops.conv3x3_up2 = real_linear, real_conv, real_conv_up2
         if dist is not None:
             dist.barrier()
-        launches = _lib.launch_count()
-        clocks = sampler.stop() if rank == 0 else None
+        res["launches"] = _lib.launch_count()
+        res["clocks"] = sampler.stop() if rank == 0 else None
         elapsed_ms = t0.elapsed_time(t1)
+        res["rank_ms_per_step"] = elapsed_ms / steps
         if dist is not None:
             tmax = torch.tensor([elapsed_ms], device=dev)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            elapsed_ms = float(tmax.item())
-        gemm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
-        gemm_flops = sum(f for _, _, f in gemm_events)
-        n_gemm = len(gemm_events)
+            tall = torch.empty(world, device=dev)
+            dist.all_gather_into_tensor(tall, tmax)
+            res["per_rank_ms_per_step"] = [round(float(v) / steps, 3) for v in tall.tolist()]
+            elapsed_ms = float(tall.max().item())
+        res["elapsed_ms"] = elapsed_ms
+        res["gemm_ms"] = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
+        res["gemm_flops"] = sum(f for _, _, f in gemm_events)
+        res["n_gemm"] = len(gemm_events)
 
         # ---- e2e: pinned host images in, host logits out, through the public host-to-host call -----------------
-        # spegnet_b200.HostPipeline: every step's 201 MB host->device copy and 68 MB device->host read are inside the
-        # timed region, on their own streams (copy of batch i+1 / read-back of batch i-1 overlap the kernels of batch i)
-        from spegnet_b200.pipeline import HostPipeline
-
+        # spegnet_b200.HostPipeline: every step's host->device copy and device->host read are inside the timed
+        # region, on their own streams (copy of batch i+1 / read-back of batch i-1 overlap the kernels of batch i)
         host_in = [torch.randn(B, 3, S, S).pin_memory() for _ in range(2)]
         pipe = HostPipeline(model, dev)
         checksum = 0.0
@@ -389,7 +419,6 @@ def main():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        e2e_steps = max(3, min(args.steps, 10))
         w0 = time.perf_counter()
         for out in pipe.run(host_in[i % 2] for i in range(e2e_steps)):
             checksum += float(out["prediction"][0, 0, 0, 0])
@@ -399,11 +428,73 @@ def main():
             tmax = torch.tensor([e2e_ms], device=dev)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             e2e_ms = float(tmax.item())
+        res["e2e_ms"] = e2e_ms
+        res["e2e_steps"] = e2e_steps
+        res["x1"] = batches[0][:1].contiguous()
+    return res
 
-        # ---- p50 batch-1 latency (the second half of BASELINE's metric) ---------------------------------
-        latency = None
-        if rank == 0 and not args.no_latency:
-            x1 = batches[0][:1].contiguous()
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE config 2: 64)")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--dtype", default=os.environ.get("SPEGNET_B200_DTYPE", "fp16"), choices=["fp16", "bf16"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of host CPU time for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other-dtype sub-record, the library baseline and "
+                    "the config-3 / config-4 extra keys (development runs)")
+    ap.add_argument("--dataset", type=int, default=0, help="evaluate an N-image synthetic set instead (BASELINE config 4)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.dataset > 0:
+        return run_dataset(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+
+    from spegnet_b200 import SPEGNet, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: spegnet_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        _init_nccl(dist, dev)
+    lib = _lib.load(args.dtype)
+    if lib.spg_device_check() != 0:
+        raise SystemExit(lib.spg_last_error().decode())
+
+    torch_dt = {"fp16": torch.float16, "bf16": torch.bfloat16}
+    torch.manual_seed(0)  # identical random-init weights on every rank
+    model = SPEGNet(CFG, compute_dtype=torch_dt[args.dtype])
+    extras = rank == 0 and world == 1 and not args.no_extras
+    cpu_sd = {k: v.clone() for k, v in model.state_dict().items()} if rank == 0 and world == 1 else None
+    model = model.to(dev).eval()
+
+    B, S = args.batch, args.size
+    e2e_steps = max(3, min(args.steps, 10))
+    m = measure(model, args, B, S, dev, dist, rank, world, args.steps, args.warmup, e2e_steps)
+    elapsed_ms, e2e_ms = m["elapsed_ms"], m["e2e_ms"]
+
+    # ---- p50 batch-1 latency (the second half of BASELINE's metric) ---------------------------------
+    latency = None
+    if rank == 0 and not args.no_latency:
+        with torch.no_grad():
+            x1 = m["x1"]
             for _ in range(5):
                 model(x1)
             torch.cuda.synchronize()
@@ -418,6 +509,46 @@ def main():
             lat.sort()
             latency = {"p50_ms": round(lat[len(lat) // 2], 3), "p90_ms": round(lat[int(len(lat) * 0.9)], 3), "batch": 1}
 
+    # ---- BASELINE config 4 (2026-image set, on-GPU scores) as an extra key: every rank takes part -----------
+    dataset_rec = None
+    if not args.no_extras and S == 512:
+        rec = dataset_record(model, 2026, B, S, dev, dist, rank, world, args.dtype)
+        dataset_rec = {k: rec[k] for k in ("value", "unit", "ms_per_step", "scaling", "scores", "gpu_launches")}
+        dataset_rec["workload"] = rec["config"]["workload"]
+
+    # ---- the other 16-bit storage type, same run, same weights (sub-record) --------------------------
+    other = None
+    other_name = "bf16" if args.dtype == "fp16" else "fp16"
+    if not args.no_extras:
+        del model
+        torch.cuda.empty_cache()
+        torch.manual_seed(0)
+        model2 = SPEGNet(CFG, compute_dtype=torch_dt[other_name]).to(dev).eval()
+        k2 = max(3, min(args.steps, 8))
+        m2 = measure(model2, args, B, S, dev, dist, rank, world, k2, 3, max(3, min(k2, 5)), instrument=False)
+        other = {"dtype": other_name, "value": round(world * B * k2 / (m2["elapsed_ms"] * 1e-3), 2), "unit": "images/s",
+                 "ms_per_step": round(m2["elapsed_ms"] / k2, 3), "steps": k2, "warmup": 3,
+                 "e2e": {"value": round(world * B * m2["e2e_steps"] / (m2["e2e_ms"] * 1e-3), 2), "unit": "images/s"},
+                 "parity": PARITY_NOTE[other_name]}
+        # ---- BASELINE config 3 (1024 x 1024, batch 16) as an extra key, fp16 parity build --------------
+        extra_cfg = {}
+        if extras and S == 512:
+            del model2
+            torch.cuda.empty_cache()
+            torch.manual_seed(0)
+            model3 = SPEGNet(CFG, compute_dtype=torch_dt[args.dtype]).to(dev).eval()
+            m3 = measure(model3, args, 16, 1024, dev, None, 0, 1, 5, 3, 3, instrument=False)
+            extra_cfg["config3_1024_b16"] = {
+                "value": round(16 * 5 / (m3["elapsed_ms"] * 1e-3), 2), "unit": "images/s",
+                "ms_per_step": round(m3["elapsed_ms"] / 5, 3),
+                "e2e": {"value": round(16 * m3["e2e_steps"] / (m3["e2e_ms"] * 1e-3), 2), "unit": "images/s"},
+                "frac_of_sustained_peak": None, "dtype": args.dtype,
+                "workload": "SPEGNet inference forward, batch 16, 1024x1024 (BASELINE config 3)"}
+            del model3
+            torch.cuda.empty_cache()
+    else:
+        extra_cfg = {}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -429,38 +560,59 @@ def main():
     value = images / (elapsed_ms * 1e-3)
     ms_per_step = elapsed_ms / args.steps
     gflop_img = GFLOP_PER_IMAGE.get(S, GFLOP_PER_IMAGE[512] * (S / 512.0) ** 2)
-    achieved_tf = gemm_flops / (gemm_ms * 1e-3) * 1e-12
+    achieved_tf = m["gemm_flops"] / (m["gemm_ms"] * 1e-3) * 1e-12
     model_tf = gflop_img * 1e9 * B / (ms_per_step * 1e-3) * 1e-12  # per GPU
     e2e_value = world * B * e2e_steps / (e2e_ms * 1e-3)
+    if "config3_1024_b16" in extra_cfg:
+        c3 = extra_cfg["config3_1024_b16"]
+        c3["frac_of_sustained_peak"] = round(GFLOP_PER_IMAGE[1024] * 1e9 * c3["value"] * 1e-12 / peak_tf, 4)
 
     line = {
         "metric": "images_per_sec", "value": round(value, 2), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": f"SPEGNet inference forward, batch {B}/GPU, {S}x{S}, Hiera-L trunk + CFI/EFE/PED head, "
-                               "random-init weights (BASELINE config 2)",
+                               "random-init weights" + (" (BASELINE config 2)" if (B, S) == (64, 512) else
+                                                        " (BASELINE config 3)" if (B, S) == (16, 1024) else ""),
                    "batch_per_gpu": B, "size": S, "parallelism": f"batch-sharded x{world}",
                    "l2": "3 rotating input batches; per-step activation working set >> 126 MB L2",
-                   "storage_dtype": args.dtype, "accumulate": "fp32 (TMEM)", "residual_stream": "fp32"},
+                   "storage_dtype": args.dtype, "accumulate": "fp32 (TMEM)", "residual_stream": "fp32",
+                   "collective": "one all_gather of the per-image integer MAE partials of all steps at the end of the "
+                                 "timed region (inside it); no per-step rendezvous",
+                   "parity": PARITY_NOTE[args.dtype]},
         "e2e": {"value": round(e2e_value, 2), "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S * 4,
                 "d2h_bytes_per_step": B * (S * S + (S // 8) ** 2) * 4, "steps": e2e_steps,
                 "call": "HostPipeline(model).run(pinned host batches) -> pinned host logits + edge maps, copies on their own streams"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(m["launches"]),
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all Linear / 1x1 / 3x3-conv launches)",
                      "achieved": round(achieved_tf, 1), "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": round(achieved_tf / peak_tf, 4),
                      "traffic": NCU_TRAFFIC["bytes_per_launch"] if (B == 64 and S == 512) else None,
                      "traffic_detail": NCU_TRAFFIC, "peak_source": f"{peak_src} sustained bf16",
-                     "launches_per_step": n_gemm // max(args.steps, 1), "kernel_ms_per_step": round(gemm_ms / args.steps, 3),
-                     "share_of_step": round(gemm_ms / elapsed_ms, 4)},
+                     "launches_per_step": m["n_gemm"] // max(args.steps, 1),
+                     "kernel_ms_per_step": round(m["gemm_ms"] / args.steps, 3),
+                     "share_of_step": round(m["gemm_ms"] / (m["rank_ms_per_step"] * args.steps), 4)},
         "model_roofline": {"gflop_per_image": gflop_img, "achieved_tflops_per_gpu": round(model_tf, 1),
                            "frac_of_sustained_peak": round(model_tf / peak_tf, 4),
                            "note": "algorithmic FLOPs of the reference formulation (SURVEY.md 8(d)) / whole step time"},
-        "clocks": clocks,
+        "clocks": m["clocks"],
     }
+    if "per_rank_ms_per_step" in m:
+        line["per_rank_ms_per_step"] = m["per_rank_ms_per_step"]
+    if other is not None:
+        line[other_name] = other
     if latency is not None:
         line["latency_b1"] = latency
-    if cpu_sd is not None:
+    if dataset_rec is not None:
+        extra_cfg["config4_dataset2026"] = dataset_rec
+    if extra_cfg:
+        line["extra_configs"] = extra_cfg
+    if extras and cpu_sd is not None:
+        lib_base = gpu_library_rate(cpu_sd, B, S, dev)
+        line["gpu_library_baseline"] = lib_base
+        line["vs_library"] = {k: (round(value / v["value"], 2) if v.get("value") else None)
+                              for k, v in lib_base.items() if isinstance(v, dict)}
+    if cpu_sd is not None and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_rate(cpu_sd, S, args.cpu_budget, 12)
     else:
         line["cpu_baseline"] = None

@@ -38,6 +38,7 @@ class HostPipeline:
     def _stage_in(self, slot: int, host: torch.Tensor) -> torch.cuda.Event:
         buf = self._dev_in[slot]
         fresh = buf is None or buf.shape != host.shape
+        compute = torch.cuda.current_stream(self.device)  # taken BEFORE switching to the copy stream below
         if fresh:
             buf = torch.empty(host.shape, dtype=torch.float32, device=self.device)
             self._dev_in[slot] = buf
@@ -46,7 +47,7 @@ class HostPipeline:
                 # The block comes from the caching allocator of the COMPUTE stream and may have just been released by
                 # kernels that are still queued there (an earlier forward's workspace or outputs): the copy stream must
                 # not write it before everything enqueued on the compute stream so far has run.
-                self.s_in.wait_stream(torch.cuda.current_stream(self.device))
+                self.s_in.wait_stream(compute)
             elif self._fwd_done[slot] is not None:  # the forward that last read this buffer must be done
                 self.s_in.wait_event(self._fwd_done[slot])
             buf.copy_(host, non_blocking=True)

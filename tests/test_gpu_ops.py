@@ -9,9 +9,11 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-# Every test runs against both library variants (libspegnet_b200_fp16.so / _bf16.so).  Tolerances are
-# written for bf16 (2^-8 relative output rounding); fp16 is 8x tighter and must pass them a fortiori.
+# Every test runs against both library variants (libspegnet_b200_fp16.so / _bf16.so).  Tolerances at the call
+# sites are written for bf16 (2^-8 relative output rounding); a 16-bit result of the fp16 build is held to an
+# 8x tighter bound (2^-11 rounding), so an fp16-only regression cannot hide behind the bf16 bound.
 H16 = torch.bfloat16
+FP16_TIGHTEN = 8.0
 
 
 @pytest.fixture(scope="module", params=["fp16", "bf16"])
@@ -32,6 +34,8 @@ def _bf(t):
 
 
 def _close(got, ref, atol, rtol):
+    if got.dtype == torch.float16:
+        atol, rtol = atol / FP16_TIGHTEN, rtol / FP16_TIGHTEN
     got, ref = got.float(), ref.float()
     err = (got - ref).abs()
     tol = atol + rtol * ref.abs()
@@ -379,3 +383,27 @@ def test_tcgen05_attention_kernels_directly(ops, B, H, heads, ws):
     ops.window_attention_tc(qkv, out, B, H, H, D, heads, ws, False)
     ref = _ref_attention(qkv, B, H, D, heads, ws, False)
     _close(out.view(B, H, H, D), ref, 2e-2, 2e-2)
+
+
+def test_fp16_stores_saturate(ops):
+    """Every 16-bit store converts with .satfinite (csrc/half16.cuh): an accumulator beyond the fp16 range becomes
+    +-65504, never inf (which the next LayerNorm / softmax would turn into NaN).  bf16 has fp32's range: finite too."""
+    M, N, K = 128, 64, 64
+    a = torch.full((M, K), 1000.0, device="cuda").to(H16)
+    w = torch.full((N, K), 100.0, device="cuda").to(H16)
+    w[N // 2:] *= -1
+    out = torch.empty(M, N, device="cuda", dtype=H16)
+    ops.linear(a, w, out)
+    assert bool(torch.isfinite(out.float()).all())
+    if H16 == torch.float16:
+        assert float(out.float().max()) == 65504.0 and float(out.float().min()) == -65504.0
+    else:
+        _close(out, a.float() @ w.float().t(), 0.0, 1e-2)
+    y = torch.empty(8, 144, device="cuda", dtype=H16)
+    x = torch.zeros(8, 144, device="cuda")
+    x[:, 0] = 1.0
+    ops.layernorm(x, torch.full((144,), 1e4, device="cuda"), torch.zeros(144, device="cuda"), y, 1e-6)  # 1e4 * 11.96
+    assert bool(torch.isfinite(y.float()).all())
+    z = torch.empty(1024, device="cuda", dtype=H16)
+    ops.cast_h16(torch.full((1024,), 1e6, device="cuda"), z)
+    assert bool(torch.isfinite(z.float()).all())
