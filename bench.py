@@ -274,8 +274,10 @@ def gpu_library_rate(state_dict, B: int, S: int, dev, iters: int = 3):
     cpu_baseline: the oracle is the thing timed here, never the product."""
     import torch
 
+    import oracle.hiera as oracle_hiera
     from oracle.spegnet import spegnet_forward
 
+    oracle_hiera.ATTENTION_IMPL = "sdpa"  # the fused library attention, as upstream sam2 calls it
     sd = {k: v.to(dev) for k, v in state_dict.items()}
     x = torch.randn(B, 3, S, S, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
     out = {}
@@ -305,7 +307,8 @@ def gpu_library_rate(state_dict, B: int, S: int, dev, iters: int = 3):
         torch.cuda.empty_cache()
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    out["what"] = (f"oracle port of SPEGNet.forward on cuda (eager torch {torch.__version__}: cuBLAS / cuDNN / ATen), "
+    oracle_hiera.ATTENTION_IMPL = "einsum"
+    out["what"] = (f"oracle port of SPEGNet.forward on cuda (eager torch {torch.__version__}: cuBLAS / cuDNN / SDPA / ATen), "
                    f"batch {B}, {S}x{S}, {iters} timed forwards, CUDA events")
     return out
 

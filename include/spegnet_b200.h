@@ -107,6 +107,19 @@ typedef struct spg_epilogue {
     float* ln_emit_rec;       /* producer: [M][32] fp32 row records of out */
     const float* ln_prev_rec; /* producer: records of the residual input rows, or NULL */
     void* ln_emit_out;        /* producer: [M, N] 16-bit centred copy of out */
+    /*
+     * LayerNorm APPLIED by the producer (the default trunk path): besides out (the fp32 residual stream, needs
+     * residual != NULL) the GEMM stores ln_apply_out[M, N] = LayerNorm(out) * ln_apply_gamma + ln_apply_beta as 16 bit
+     * (eps = ln_eps) -- the operand of the next block's qkv / MLP GEMMs, so no separate LayerNorm pass over HBM exists.
+     * The CTAs (or CTA pairs) that hold the n-tiles of one 128-row block are launched as one thread-block cluster: each
+     * epilogue thread parks its final fp32 values in the consumed TMEM accumulator columns, publishes {mean, M2} of its
+     * column slice to its peers' shared memory (st.shared::cluster + mbarrier), combines the slices in fixed column
+     * order (Chan's formula; independent of M and of the grid) and normalises in a second pass over TMEM.
+     * N must be 144, 288 or 576 (one, two or three n-tiles); no activation, no head.
+     */
+    const float* ln_apply_gamma; /* [N] fp32 or NULL */
+    const float* ln_apply_beta;  /* [N] fp32 */
+    void* ln_apply_out;          /* [M, N] 16-bit */
 } spg_epilogue_t;
 
 /*

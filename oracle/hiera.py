@@ -100,6 +100,9 @@ def block_specs(cfg: HieraConfig) -> List[BlockSpec]:
     return specs
 
 
+ATTENTION_IMPL = "einsum"  # "sdpa": F.scaled_dot_product_attention (library baseline on the GPU)
+
+
 def _pool2x2_nhwc(t: torch.Tensor, stride: int) -> torch.Tensor:
     return F.max_pool2d(t.permute(0, 3, 1, 2), kernel_size=stride, stride=stride).permute(0, 2, 3, 1)
 
@@ -148,9 +151,15 @@ def block_forward(sd: Dict[str, torch.Tensor], pre: str, x: torch.Tensor, spec: 
         q = _pool2x2_nhwc(q.reshape(nw, ws, ws, spec.dim_out), spec.q_stride)
         ws_out = ws // spec.q_stride
         q = q.reshape(nw, ws_out * ws_out, spec.heads, hd)
-    scores = torch.einsum("wqhd,wkhd->whqk", q, k) * (1.0 / math.sqrt(hd))
-    probs = scores.softmax(dim=-1)
-    ctx = torch.einsum("whqk,wkhd->wqhd", probs, v).reshape(nw, ws_out, ws_out, spec.dim_out)
+    if ATTENTION_IMPL == "sdpa":
+        # upstream sam2 calls F.scaled_dot_product_attention; only the GPU library-baseline leg of bench.py selects it
+        # (the fused kernel is what the reference would run on a GPU); the CPU oracle keeps the explicit softmax
+        ctx = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)).transpose(1, 2)
+        ctx = ctx.reshape(nw, ws_out, ws_out, spec.dim_out)
+    else:
+        scores = torch.einsum("wqhd,wkhd->whqk", q, k) * (1.0 / math.sqrt(hd))
+        probs = scores.softmax(dim=-1)
+        ctx = torch.einsum("whqk,wkhd->wqhd", probs, v).reshape(nw, ws_out, ws_out, spec.dim_out)
     ctx = F.linear(ctx, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
     ho, wo = (h // spec.q_stride, w // spec.q_stride) if spec.q_stride else (h, w)
     x = skip + _from_windows(ctx, ws_out, b, ho, wo)

@@ -31,6 +31,7 @@ class Epilogue(C.Structure):
         ("head_out", C.c_void_p),
         ("ln_fold_rec", C.c_void_p), ("ln_fold_cw", C.c_void_p), ("ln_cols", C.c_int), ("ln_eps", C.c_float),
         ("ln_emit_rec", C.c_void_p), ("ln_prev_rec", C.c_void_p), ("ln_emit_out", C.c_void_p),
+        ("ln_apply_gamma", C.c_void_p), ("ln_apply_beta", C.c_void_p), ("ln_apply_out", C.c_void_p),
     ]
 
 

@@ -49,9 +49,15 @@ constexpr int kAccStageCols = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarBytes = 1024;                                // pipeline barriers + residual barriers
-constexpr int kEpiScratch = (2 * 256 + 256 + 3 * 128 + 2 * 256) * 4;  // bias[2][256], head weights[256], head partials[3][128], LN column sums[2][256]
+constexpr int kEpiScratch = (2 * 256 + 256 + 3 * 128 + 2 * 256 + 2 * 256) * 4;  // bias[2][256], head weights[256], head partials[3][128], LN column sums / gamma[2][256], LN beta[2][256]
 constexpr int kLnRec = 32;                                      // floats per LayerNorm row record {c, P, (s1, s2) x P}
 constexpr int kLnBufBytes = 32 * 32;                            // staging buffer of the 16-bit centred copy: 32 rows x 16 columns
+// LayerNorm applied by the producer (kLn == 3): staging ring of the normalised 16-bit rows per epilogue warp, and the
+// exchange area of the per-(n-tile, column slice) row statistics {mean, M2} that the CTAs of a cluster write into each
+// other's shared memory (double-buffered across tiles)
+constexpr int kLnSlots = 2;
+constexpr int kLnMaxParts = 6;
+constexpr int kLnXBytes = 2 * kLnMaxParts * kBlockM * 8;
 #ifndef SPG_RES_SLOTS
 #define SPG_RES_SLOTS 3
 #endif
@@ -100,7 +106,11 @@ struct GemmArgs {
     float* ln_emit_rec;
     const float* ln_prev_rec;
     float ln_inv_cols, ln_eps;
-    int ln_mode;      // 0 none, 1 consumer (fold), 2 producer (emit): selects the kernel instance
+    int ln_mode;      // 0 none, 1 consumer (fold), 2 producer (emit), 3 producer that applies the LayerNorm itself
+    // ln_mode 3: out = fp32 residual stream as usual, plus y = LayerNorm(out) * gamma + beta stored as 16 bit through
+    // tmap_ln.  The CTAs that hold the n-tiles of one 128-row block form a cluster and exchange row statistics.
+    const float* ln_gamma;
+    const float* ln_beta;
 };
 
 #ifdef SPG_TRACE
@@ -156,7 +166,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     const uint32_t tiles_addr = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
-    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+    // cluster rank; a cluster is one CTA pair, or (kLn == 3) every CTA / pair holding an n-tile of the same row block
+    const uint32_t crank = (kPair || kLn == 3) ? cluster_ctarank() : 0u;
+    const uint32_t rank = kPair ? (crank & 1u) : 0u;  // position inside the CTA pair
     const bool leader = rank == 0;
     // bytes of ONE weight tile held by this CTA (pair mode: half of the block_n rows)
     const uint32_t b_stage_bytes = static_cast<uint32_t>(kPair ? p.block_n / 2 : p.block_n) * 128u;
@@ -170,6 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     auto tmem_empty_bar = [&](int a) { return bar_addr + 8u * (2 * p.stages + 2 + a); };
     const uint32_t tmem_slot = bar_addr + 8u * (2 * p.stages + 4);
     auto res_bar = [&](int ew, int slot) { return bar_addr + 256u + 8u * (ew * kResSlots + slot); };
+    auto ln_bar = [&](int b) { return bar_addr + 768u + 8u * b; };  // kLn == 3: statistics of tile parity b have arrived
     const uint32_t scratch_addr = bar_addr + kBarBytes;
     const uint32_t staging_addr = (scratch_addr + kEpiScratch + 1023u) & ~1023u;  // 128B-swizzle atoms: 1 KB aligned
 
@@ -196,6 +209,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int ew = 0; ew < kEpiWarps; ++ew)
             for (int s = 0; s < kResSlots; ++s) mbar_init(res_bar(ew, s), 1);
+        if (kLn == 3)  // every epilogue thread of every CTA holding an n-tile of the row block arrives once per tile
+            for (int b = 0; b < 2; ++b) mbar_init(ln_bar(b), static_cast<uint32_t>(p.num_n_tiles) * 32u * kEpiWarps);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -209,7 +224,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     pdl_launch_dependents();
     tc_fence_before();
-    if (kPair) cluster_sync_all();  // the peer's barriers / TMEM must exist before any remote arrive or 2-CTA MMA
+    if (kPair || kLn == 3) cluster_sync_all();  // the peers' barriers / TMEM must exist before any remote arrive or 2-CTA MMA
     else __syncthreads();
     tc_fence_after();
     pdl_wait();  // prologue done (barriers, TMEM, descriptor prefetch); operands of the previous kernel are read below
@@ -313,7 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 else umma_bf16_ss(d, a, b, idesc, accum);
             };
             auto commit = [&](uint32_t bar) {
-                if (kPair) umma_commit_pair(bar);
+                if (kPair) umma_commit_pair(bar, static_cast<uint16_t>(3u << (crank & ~1u)));
                 else umma_commit(bar);
             };
             int stage = 0;
@@ -397,11 +412,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         float* bias_s = reinterpret_cast<float*>(smem_raw + (scratch_addr - raw_addr));
         float* headw_s = bias_s + 2 * 256;
         float* headp_s = headw_s + 256;
-        float* cw_s = headp_s + 3 * 128;  // [2][256] column sums of W' (kLn == 1)
+        float* cw_s = headp_s + 3 * 128;  // [2][256] column sums of W' (kLn == 1) / LayerNorm gamma (kLn == 3)
+        float* lnb_s = cw_s + 2 * 256;    // [2][256] LayerNorm beta (kLn == 3)
         const uint32_t my_staging = staging_addr + ewarp * kResSlots * p.buf_bytes;
         // kLn == 2: ring of 1 KB buffers for the 16-bit centred copy, slot-locked to the main ring
         const uint32_t my_ln_staging = staging_addr + kEpiWarps * kResSlots * p.buf_bytes + ewarp * kResSlots * kLnBufBytes;
         uint8_t* my_ln_staging_ptr = smem_raw + (my_ln_staging - raw_addr);
+        // kLn == 3: own ring of kLnSlots 1 KB buffers for the normalised rows, then the statistics exchange area
+        const uint32_t ln3_base = staging_addr + kEpiWarps * kResSlots * p.buf_bytes;
+        const uint32_t my_ln3_staging = ln3_base + ewarp * kLnSlots * kLnBufBytes;
+        uint8_t* my_ln3_staging_ptr = smem_raw + (my_ln3_staging - raw_addr);
+        const uint32_t ln_x_addr = ln3_base + kEpiWarps * kLnSlots * kLnBufBytes;  // float2 [2][kLnMaxParts][128]
+        const float2* ln_x_ptr = reinterpret_cast<const float2*>(smem_raw + (ln_x_addr - raw_addr));
+        int ln_buf = 0, ln_slot = 0;
+        uint32_t ln_phase = 0;  // bit b = parity of ln_bar(b)
         uint8_t* my_staging_ptr = smem_raw + (my_staging - raw_addr);
         // Staging buffer = 32 rows x (group x 16) columns of the output type, rows of 32 / 64 / 128 bytes in
         // the matching TMA swizzle (32B / 64B / 128B): 16-byte piece j of row r sits at j ^ ((r >> shift) & mask),
@@ -420,7 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int slot = 0;
         uint32_t res_parity = 0;
         // the accumulator stage is handed back on the LEADER's tmem_empty barrier (the leader issues the MMAs)
-        const uint32_t tmem_empty_remote0 = kPair ? mapa_shared(tmem_empty_bar(0), 0) : 0u;
+        const uint32_t tmem_empty_remote0 = kPair ? mapa_shared(tmem_empty_bar(0), crank & ~1u) : 0u;
         [[maybe_unused]] int trace_i = 0;
         for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
             if (ewarp == 0 && lane == 0) SPG_STAMP(trace_i, 6);
@@ -458,6 +482,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if (etid < p.block_n) bs[etid] = (p.bias != nullptr && n0 + etid < p.N) ? __ldg(p.bias + n0 + etid) : 0.f;
             float* cws = cw_s + buf * 256;
             if (kLn == 1 && etid < p.block_n) cws[etid] = n0 + etid < p.N ? __ldg(p.ln_fold_cw + n0 + etid) : 0.f;
+            float* lnbs = lnb_s + buf * 256;
+            if (kLn == 3 && etid < p.block_n) {
+                cws[etid] = __ldg(p.ln_gamma + n0 + etid);  // N % block_n == 0 in this mode
+                lnbs[etid] = __ldg(p.ln_beta + n0 + etid);
+            }
+            float ln3_shift = 0.f;
             // LayerNorm folding: this thread's row statistics (consumer) or centre (producer), from the row records
             const int ln_row = row0 + lane;
             float ln_rs = 1.f, ln_rm = 0.f, ln_c = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;
@@ -570,6 +600,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         v[4 * i + 3] += r.w;
                     }
                 }
+                if (kLn == 3) {  // v = the row's new residual-stream values: statistics now, normalisation in pass 2
+                    if (c == c_begin) ln3_shift = v[0];
+                    uint32_t wb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float d = v[i] - ln3_shift;  // shifted sums: no cancellation in M2 = s2 - s1^2 / n
+                        ln_s1 += d;
+                        ln_s2 = fmaf(d, d, ln_s2);
+                        wb[i] = __float_as_uint(v[i]);
+                    }
+                    tmem_st16(taddr + c * 16, wb);  // park v over the consumed accumulator columns
+                }
                 if (kLn == 2) {  // centred 16-bit copy for the consumer GEMMs + this thread's partial row statistics
                     float vc[16];
 #pragma unroll
@@ -648,6 +690,88 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     process(rb, c + 1, !pair, true);
                 }
             }
+            if (kLn == 3) {
+                // ---- exchange {mean, M2} of this thread's column slice with every CTA that holds an n-tile of the row
+                // block (cluster peers; in pair mode the CTAs with the same pair rank), combine in fixed (n-tile, slice)
+                // order -> statistics that do not depend on M, on the grid or on which CTA computed what
+                const int chunks_all = p.block_n >> 4;
+                const int units_all = (chunks_all + p.group - 1) / p.group;
+                auto slice_cols = [&](int pt) {
+                    const int b = pt == 0 ? 0 : min(chunks_all, p.group * ((units_all * pt + kParts - 1) / kParts));
+                    const int e = pt == kParts - 1 ? chunks_all : min(chunks_all, p.group * ((units_all * (pt + 1) + kParts - 1) / kParts));
+                    return static_cast<float>((e - b) * 16);
+                };
+                const float n_i = static_cast<float>(n_my * 16);
+                const float mean_i = n_my > 0 ? ln3_shift + ln_s1 / n_i : 0.f;
+                const float m2_i = n_my > 0 ? fmaxf(ln_s2 - ln_s1 * ln_s1 / n_i, 0.f) : 0.f;
+                const uint32_t my_x = ln_x_addr + static_cast<uint32_t>(((ln_buf * kLnMaxParts + n_blk * kParts + part) * kBlockM + row_in_tile) * 8);
+                for (int j = 0; j < p.num_n_tiles; ++j) {
+                    const uint32_t peer = kPair ? static_cast<uint32_t>(2 * j) + rank : static_cast<uint32_t>(j);
+                    st_cluster_f32x2(mapa_shared(my_x, peer), mean_i, m2_i);
+                }
+                for (int j = 0; j < p.num_n_tiles; ++j) {
+                    const uint32_t peer = kPair ? static_cast<uint32_t>(2 * j) + rank : static_cast<uint32_t>(j);
+                    mbar_arrive_cluster(mapa_shared(ln_bar(ln_buf), peer));
+                }
+                tmem_st_wait();
+                mbar_wait_cluster(ln_bar(ln_buf), (ln_phase >> ln_buf) & 1u);
+                ln_phase ^= 1u << ln_buf;
+                const float2* px = ln_x_ptr + (ln_buf * kLnMaxParts) * kBlockM + row_in_tile;
+                const int nparts = p.num_n_tiles * kParts;
+                float mean = 0.f;
+                for (int q = 0; q < nparts; ++q) mean = fmaf(slice_cols(q % kParts), px[q * kBlockM].x, mean);
+                mean *= p.ln_inv_cols;
+                float m2 = 0.f;
+                for (int q = 0; q < nparts; ++q) {
+                    const float2 st = px[q * kBlockM];
+                    const float d = st.x - mean;
+                    m2 += fmaf(slice_cols(q % kParts) * d, d, st.y);
+                }
+                const float rstd = rsqrtf(m2 * p.ln_inv_cols + p.ln_eps);
+                const float mr = -mean * rstd;
+                ln_buf ^= 1;
+                // ---- pass 2: y = (v - mean) * rstd * gamma + beta, 16 bit, staged per 16-column chunk and TMA-stored
+                uint32_t ya[16], yb[16];
+                auto emit = [&](const uint32_t (&raw)[16], int c) {
+                    const int col = c * 16;
+                    if (lane == 0) tma_store_wait_read<kLnSlots - 1>();  // the store that last read this slot is done
+                    __syncwarp();
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 g = reinterpret_cast<const float4*>(cws + col)[i];
+                        const float4 b = reinterpret_cast<const float4*>(lnbs + col)[i];
+                        y[4 * i + 0] = fmaf(fmaf(__uint_as_float(raw[4 * i + 0]), rstd, mr), g.x, b.x);
+                        y[4 * i + 1] = fmaf(fmaf(__uint_as_float(raw[4 * i + 1]), rstd, mr), g.y, b.y);
+                        y[4 * i + 2] = fmaf(fmaf(__uint_as_float(raw[4 * i + 2]), rstd, mr), g.z, b.z);
+                        y[4 * i + 3] = fmaf(fmaf(__uint_as_float(raw[4 * i + 3]), rstd, mr), g.w, b.w);
+                    }
+                    uint8_t* lst = my_ln3_staging_ptr + ln_slot * kLnBufBytes + lane * 32;
+                    const uint32_t lx = (lane >> 2) & 1u;  // 32-byte swizzle: the two 16-byte pieces swap on rows 4..7 of 8
+                    *reinterpret_cast<uint4*>(lst + ((0u ^ lx) << 4)) =
+                        make_uint4(pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+                    *reinterpret_cast<uint4*>(lst + ((1u ^ lx) << 4)) =
+                        make_uint4(pack2(y[8], y[9]), pack2(y[10], y[11]), pack2(y[12], y[13]), pack2(y[14], y[15]));
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_ln, my_ln3_staging + ln_slot * kLnBufBytes, n0 + col, row0);
+                        tma_store_commit();
+                    }
+                    ln_slot = ln_slot == kLnSlots - 1 ? 0 : ln_slot + 1;
+                };
+                if (n_my > 0) tmem_ld16(taddr + c_begin * 16, ya);
+                for (int c = c_begin; c < c_end; c += 2) {
+                    tmem_ld_wait();
+                    if (c + 1 < c_end) tmem_ld16(taddr + (c + 1) * 16, yb);
+                    emit(ya, c);
+                    if (c + 1 < c_end) {
+                        tmem_ld_wait();
+                        if (c + 2 < c_end) tmem_ld16(taddr + (c + 2) * 16, ya);
+                        emit(yb, c + 1);
+                    }
+                }
+            }
             if (kLn == 2 && ln_row < p.M) {  // row record: fixed slot per (n-tile, column slice) -> deterministic statistics
                 float* rec = p.ln_emit_rec + static_cast<size_t>(ln_row) * kLnRec;
                 reinterpret_cast<float2*>(rec + 2)[n_blk * kParts + part] = make_float2(ln_s1, ln_s2);
@@ -683,7 +807,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers
         if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
     } else {
-        __syncthreads();
+        if (kLn == 3) cluster_sync_all();  // peers may still be writing statistics into this CTA's shared memory
+        else __syncthreads();
         if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
     }
 }
@@ -744,7 +869,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
     const int stage_bytes = a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128;
     const int staging = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
-                        (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0);
+                        (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0) +
+                        (a.ln_mode == 3 ? a.epi_warps * kLnSlots * kLnBufBytes + kLnXBytes : 0);
     const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
@@ -753,6 +879,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     a.stages = stages;
     const int smem = stages * stage_bytes + fixed;
     const int sms = sm_count();
+    // ln_mode 3: the CTAs / pairs holding the n-tiles of one row block form the cluster
+    const int cluster = (pair ? 2 : 1) * (a.ln_mode == 3 ? a.num_n_tiles : 1);
     int grid;
     if (pair) {
         const int units = ((a.num_m_tiles + 1) / 2) * a.num_n_tiles;
@@ -760,6 +888,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     } else {
         grid = total_1cta < sms ? total_1cta : sms;
     }
+    grid -= grid % cluster;  // whole clusters only (total tiles are a multiple of the n-tiles per row block)
     const bool head = a.head_w != nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -768,7 +897,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     cfg.stream = ctx.stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = pair ? 2 : 1;
+    attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see common.h "Programmatic dependent launch"
@@ -823,6 +952,27 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
         else SPG_LAUNCH_LN(SPG_ACT_NONE, 0, 0, 1);
     } else if (a.ln_mode == 2) {  // LayerNorm producer: fp32 residual GEMM that also emits the centred copy + records
         SPG_LAUNCH_LN(SPG_ACT_NONE, 1, 1, 2);
+    } else if (a.ln_mode == 3) {  // LayerNorm producer that normalises itself (clusters over the n-tiles of a row block)
+        if (cluster > 2) {
+            // a persistent grid must be co-resident: cap it at what the GPCs can hold of this cluster shape
+            static int max_clusters[2][9][128] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            int& cached = max_clusters[pair ? 1 : 0][cluster][dev & 127];
+            if (cached == 0) {
+                cfg.gridDim = dim3(static_cast<unsigned>(sms - sms % cluster));
+                int n = 0;
+                auto k1 = gemm_tcgen05_kernel<SPG_ACT_NONE, 1, 1, 0, 1, 1, kEpiWarpsDefault, 0, 3>;
+                auto k0 = gemm_tcgen05_kernel<SPG_ACT_NONE, 1, 1, 0, 1, 0, kEpiWarpsDefault, 0, 3>;
+                SPG_CHECK_CUDA(cudaFuncSetAttribute(pair ? k1 : k0, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+                SPG_CHECK_CUDA(cudaFuncSetAttribute(pair ? k1 : k0, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                SPG_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, pair ? k1 : k0, &cfg));
+                cached = n > 0 ? n : 1;
+            }
+            if (grid > cached * cluster) grid = cached * cluster;
+            cfg.gridDim = dim3(grid);
+        }
+        SPG_LAUNCH_LN(SPG_ACT_NONE, 1, 1, 3);
     } else if (a.up2) {
         if (pair) SPG_LAUNCH_ONE_UP2(1);
         else SPG_LAUNCH_ONE_UP2(0);
@@ -904,7 +1054,21 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
         a.ln_emit_rec = ep->ln_emit_rec;
         a.ln_prev_rec = ep->ln_prev_rec;
     }
+    if (ep->ln_apply_out != nullptr) {
+        SPG_CHECK_ARG(a.ln_mode == 0, "ln_apply_out cannot be combined with ln_fold_rec / ln_emit_out");
+        SPG_CHECK_ARG(ep->ln_apply_gamma != nullptr && ep->ln_apply_beta != nullptr, "ln_apply_out needs gamma and beta");
+        SPG_CHECK_ARG(ep->residual != nullptr && ep->out_dtype == SPG_F32 && ep->act == SPG_ACT_NONE && ep->head_w == nullptr,
+                      "the LayerNorm producer is the fp32 residual GEMM (no activation, no head)");
+        SPG_CHECK_ARG(N % a.block_n == 0 && a.num_n_tiles * (kEpiWarpsDefault / 4) <= kLnMaxParts,
+                      "ln_apply_out: N=%d does not split into <= %d equal n-tiles", N, kLnMaxParts / (kEpiWarpsDefault / 4));
+        SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(ep->ln_apply_out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep->ln_apply_gamma) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(ep->ln_apply_beta) & 15) == 0, "LayerNorm buffers must be 16-byte aligned");
+        a.ln_mode = 3;
+        a.ln_gamma = ep->ln_apply_gamma;
+        a.ln_beta = ep->ln_apply_beta;
+    }
     a.ln_inv_cols = ep->ln_cols > 0 ? 1.0f / static_cast<float>(ep->ln_cols) : 0.f;
+    if (a.ln_mode == 3) a.ln_inv_cols = 1.0f / static_cast<float>(N);
     a.ln_eps = ep->ln_eps;
     memset(&em, 0, sizeof(em));
     if (a.has_out)
@@ -913,6 +1077,8 @@ int fill_epilogue(GemmArgs& a, EpiMaps& em, const spg_epilogue_t* ep, int M, int
         if (int rc = make_tmap_epilogue(&em.res, ep->residual, ep->res_rows > 0 ? ep->res_rows : M, N, 1, a.group * 16)) return rc;
     if (a.ln_mode == 2)
         if (int rc = make_tmap_epilogue(&em.ln, ep->ln_emit_out, M, N, 0, 16)) return rc;
+    if (a.ln_mode == 3)
+        if (int rc = make_tmap_epilogue(&em.ln, ep->ln_apply_out, M, N, 0, 16)) return rc;
     return SPG_OK;
 }
 
@@ -932,6 +1098,17 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.N = N;
     a.num_m_tiles = (M + kBlockM - 1) / kBlockM;
     a.block_n = pick_block_n(N, a.num_m_tiles, ep != nullptr && ep->head_w != nullptr ? 1 : (ep != nullptr && ep->ln_emit_out != nullptr ? 7 : 1 << 20));
+    if (ep != nullptr && ep->ln_apply_out != nullptr) {
+        // LayerNorm producer: a FIXED tiling per N (never a function of M: the row statistics are combined per
+        // (n-tile, column slice), and results must not depend on the batch size) with at most 3 equal n-tiles
+        a.block_n = 0;
+        for (int bn = 192; bn >= 16; bn -= 16)
+            if (N % bn == 0 && N / bn <= kLnMaxParts / (kEpiWarpsDefault / 4)) {
+                a.block_n = bn;
+                break;
+            }
+        SPG_CHECK_ARG(a.block_n != 0, "ln_apply_out: N=%d has no tiling into <= 3 equal n-tiles of <= 192 columns", N);
+    }
     a.num_n_tiles = (N + a.block_n - 1) / a.block_n;
     a.num_k_chunks = (K + kBlockK - 1) / kBlockK;
     a.last_chunk_ksteps = (K - (a.num_k_chunks - 1) * kBlockK + kUmmaK - 1) / kUmmaK;

@@ -284,6 +284,39 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// 8-byte store into the shared memory of any CTA of the cluster (address from mapa_shared); ordered before a later
+// mbarrier.arrive.release.cluster of the same thread
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
+}
+// wait with acquire semantics at CLUSTER scope: data written by other CTAs of the cluster before their
+// mbarrier.arrive.release.cluster is visible afterwards
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t it = 0;; ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (it > SPG_SPIN_LIMIT) {
+            printf("spg: cluster mbarrier timeout block=%d thread=%d bar=%u parity=%u\n", (int)blockIdx.x, (int)threadIdx.x, bar,
+                   parity);
+            __trap();
+        }
+    }
+}
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared address: "the leader's copy"
 
 // TMA loads issued by either CTA of a pair; the transaction bytes are signalled on the LEADER's mbarrier
@@ -327,11 +360,12 @@ __device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_de
         : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// arrives on the mbarrier at this shared offset in BOTH CTAs once all MMAs issued so far have completed
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+// arrives on the mbarrier at this shared offset in BOTH CTAs of the pair once all MMAs issued so far have completed;
+// `cta_mask` = the two cluster ranks of the pair (3 << even rank; the cluster may hold several pairs)
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask = 3) {
     asm volatile(
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-        "h"(static_cast<uint16_t>(3))
+        "h"(cta_mask)
         : "memory");
 }
 

@@ -214,6 +214,10 @@ class SPEGNet(nn.Module):
         # traffic per batch-64 step, but measured 972 vs 981 img/s at batch 64 (the residual GEMMs pay for the second
         # store and the consumers for reading the row records) and 3.00 vs 3.09 ms at batch 1, and the row statistics
         # then depend on the n-tiling, i.e. on the batch size, in the last bit.  Off by default (SPG_LN_FUSE=1 enables).
+        # Default trunk: every residual GEMM whose output feeds a LayerNorm of width 144 / 288 / 576 normalises its own
+        # rows in its epilogue (spg_epilogue_t.ln_apply_*; a cluster of the CTAs holding the row block exchanges row
+        # statistics), so stages 1-3 launch no LayerNorm kernel at all.  SPG_LN_APPLY=0 restores the separate kernels.
+        self.ln_apply = os.environ.get("SPG_LN_APPLY", "1") != "0"
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._ln_fuse = os.environ.get("SPG_LN_FUSE", "0") != "0"
         self._debug_taps: Optional[Dict[str, torch.Tensor]] = None  # tests: stream snapshot after every block
@@ -457,18 +461,33 @@ class SPEGNet(nn.Module):
         if self.ln_fuse and self._debug_taps is None and ws.rec is not None:
             return self._trunk_ln_folded(W, ws, x, B, S)
         G = S // 4
+        blocks = self.blocks
+        ends = self.spec.stage_ends
+        fused_widths = (144, 288, 576) if self.ln_apply else ()
+
+        def ln_after(width: int, gamma_key: str, rows: int):
+            """(ln_apply tuple for the producing GEMM, y) when the LayerNorm `gamma_key` over `width` channels is applied
+            by its producer; (None, y) when a separate LayerNorm launch has to follow."""
+            y = ws.y[: rows * width].view(rows, width)
+            if width in fused_widths:
+                return (W[gamma_key + ".w"], W[gamma_key + ".b"], y, LN_EPS), y
+            return None, y
+
         ops.patchify(x, ws.cols)
-        ops.linear(ws.cols, W["pe.w"], ws.x[0], bias=W["pe.b"], residual=ws.pos, res_rows=G * G)
+        # the patch embedding (+ positional embedding as a broadcast residual) feeds block 0's norm1
+        ap, y = ln_after(blocks[0].dim_in, "b0.n1", B * G * G)
+        ops.linear(ws.cols, W["pe.w"], ws.x[0], bias=W["pe.b"], residual=ws.pos, res_rows=G * G, ln_apply=ap)
+        y_ready = ap is not None
         H = G
         cur = ws.x[0]
         if self._debug_taps is not None:
             self._debug_taps["embed"] = cur.view(B, G, G, -1).clone()
-        ends = self.spec.stage_ends
-        for b in self.blocks:
+        for bi, b in enumerate(blocks):
             p = f"b{b.index}."
             M = B * H * H
             y = ws.y[: M * b.dim_in].view(M, b.dim_in)
-            ops.layernorm(cur, W[p + "n1.w"], W[p + "n1.b"], y, LN_EPS)
+            if not y_ready:
+                ops.layernorm(cur, W[p + "n1.w"], W[p + "n1.b"], y, LN_EPS)
             if b.dim_in != b.dim_out:
                 if not b.q_pool:
                     raise NotImplementedError("channel change without query pooling does not occur in Hiera-L")
@@ -484,12 +503,19 @@ class SPEGNet(nn.Module):
             ops.linear(y, W[p + "qkv.w"], qkv, bias=W[p + "qkv.b"])
             att = ws.att[: Mo * b.dim_out].view(Mo, b.dim_out)
             ops.window_attention(qkv, att, B, H, H, b.dim_out, b.heads, b.window, b.q_pool)
-            ops.linear(att, W[p + "ap.w"], nxt, bias=W[p + "ap.b"], residual=nxt)
-            z = ws.y[: Mo * b.dim_out].view(Mo, b.dim_out)
-            ops.layernorm(nxt, W[p + "n2.w"], W[p + "n2.b"], z, LN_EPS)
+            # attention projection + residual; its output feeds norm2
+            ap, z = ln_after(b.dim_out, p + "n2", Mo)
+            ops.linear(att, W[p + "ap.w"], nxt, bias=W[p + "ap.b"], residual=nxt, ln_apply=ap)
+            if ap is None:
+                ops.layernorm(nxt, W[p + "n2.w"], W[p + "n2.b"], z, LN_EPS)
             hid = ws.hid[: Mo * 4 * b.dim_out].view(Mo, 4 * b.dim_out)
             ops.linear(z, W[p + "fc1.w"], hid, bias=W[p + "fc1.b"], act=ops.ACT_GELU)
-            ops.linear(hid, W[p + "fc2.w"], nxt, bias=W[p + "fc2.b"], residual=nxt)
+            # second MLP layer + residual; its output feeds the NEXT block's norm1 (nothing after the last block)
+            ap = None
+            if bi + 1 < len(blocks):
+                ap, _ = ln_after(b.dim_out, f"b{blocks[bi + 1].index}.n1", Mo)
+            ops.linear(hid, W[p + "fc2.w"], nxt, bias=W[p + "fc2.b"], residual=nxt, ln_apply=ap)
+            y_ready = ap is not None
             cur, H = nxt, Ho
             if self._debug_taps is not None:
                 self._debug_taps[f"block{b.index}"] = cur.view(B, H, H, b.dim_out).clone()

@@ -83,7 +83,8 @@ def _ptr(t: Optional[torch.Tensor], dtype=None, name: str = "tensor") -> Optiona
     return t.data_ptr()
 
 
-def _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_fold=None, ln_emit=None) -> Epilogue:
+def _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_fold=None, ln_emit=None,
+              ln_apply=None) -> Epilogue:
     ep = Epilogue()
     ep.bias = _ptr(bias, torch.float32, "bias")
     ep.act = act
@@ -108,19 +109,26 @@ def _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_f
         ep.ln_prev_rec = _ptr(prev, torch.float32, "ln_prev_rec")
         ep.ln_emit_out = _ptr(xc, H16, "ln_emit_out")
         ep.ln_cols = int(xc.shape[1])
+    if ln_apply is not None:  # (gamma [N] fp32, beta [N] fp32, y [M,N] 16-bit, eps): the producer normalises its own rows
+        gamma, beta, y, eps = ln_apply
+        ep.ln_apply_gamma = _ptr(gamma, torch.float32, "ln_apply_gamma")
+        ep.ln_apply_beta = _ptr(beta, torch.float32, "ln_apply_beta")
+        ep.ln_apply_out = _ptr(y, H16, "ln_apply_out")
+        ep.ln_eps = float(eps)
     return ep
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, out: Optional[torch.Tensor], *, bias=None, act=ACT_NONE,
            residual=None, res_rows: int = 0, head_w=None, head_b: float = 0.0, head_out=None, ln_fold=None,
-           ln_emit=None) -> None:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; see spg_linear_h16.  `ln_fold` / `ln_emit` fold the
-    LayerNorm between a residual GEMM (producer) and the GEMMs reading its output (consumers), see spg_epilogue_t."""
+           ln_emit=None, ln_apply=None) -> None:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T); a, w bf16; see spg_linear_h16.  `ln_apply` = (gamma, beta, y, eps) makes a
+    residual GEMM also store y = LayerNorm(out) (the next GEMMs' operand; no separate LayerNorm pass).  `ln_fold` /
+    `ln_emit` are the older folded formulation (opt-in), see spg_epilogue_t."""
     M, K = a.shape
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f"weight K {w.shape[1]} != activation K {K}")
-    ep = _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_fold, ln_emit)
+    ep = _epilogue(out, bias, act, residual, res_rows, head_w, head_b, head_out, ln_fold, ln_emit, ln_apply)
     lib, dn = _lib_for(a)
     rc = lib.spg_linear_h16(_ptr(a, H16, "a"), _ptr(w, H16, "w"), M, N, K,
                                      C.byref(ep), _launch(True))

@@ -407,3 +407,36 @@ def test_fp16_stores_saturate(ops):
     z = torch.empty(1024, device="cuda", dtype=H16)
     ops.cast_h16(torch.full((1024,), 1e6, device="cuda"), z)
     assert bool(torch.isfinite(z.float()).all())
+
+
+@pytest.mark.parametrize("M,N,K,res_rows", [(16384, 576, 2304, 0), (16384, 576, 576, 0), (1000, 576, 576, 0),
+                                            (4096, 288, 1152, 0), (20000, 288, 288, 0), (2000, 144, 576, 0),
+                                            (4096, 144, 168, 1024), (128, 576, 2304, 0)])
+def test_layernorm_applied_by_the_producer(ops, M, N, K, res_rows):
+    """spg_epilogue_t.ln_apply_*: the residual GEMM stores the fp32 stream AND y = LayerNorm(stream) * gamma + beta as
+    16 bit; the CTAs (pairs for long K) holding the n-tiles of a row block exchange row statistics through distributed
+    shared memory.  Covers clusters of 1 / 2 / 3 CTAs and of 3 CTA pairs, a ragged last row block and the broadcast
+    residual of the patch embedding."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(res_rows or M, N, device="cuda", generator=g) * 2 + 0.7
+    gamma = torch.rand(N, device="cuda", generator=g) + 0.5
+    beta = torch.randn(N, device="cuda", generator=g)
+    ref_x = a.float() @ w.float().t() + bias + (res.repeat(M // res_rows, 1) if res_rows else res)
+    out = torch.empty(M, N, device="cuda") if res_rows else res.clone()
+    y = torch.full((M, N), float("nan"), device="cuda", dtype=H16)
+    ops.linear(a, w, out, bias=bias, residual=res if res_rows else out, res_rows=res_rows, ln_apply=(gamma, beta, y, 1e-6))
+    _close(out, ref_x, 3e-4, 1e-4)
+    _close(y, F.layer_norm(ref_x, (N,), gamma, beta, 1e-6), 2e-2, 1e-2)
+    # the statistics are combined in a fixed order: a second launch and a launch over a row subset give the same bits
+    out2 = torch.empty(M, N, device="cuda") if res_rows else res.clone()
+    y2 = torch.empty_like(y)
+    ops.linear(a, w, out2, bias=bias, residual=res if res_rows else out2, res_rows=res_rows, ln_apply=(gamma, beta, y2, 1e-6))
+    assert torch.equal(y, y2)
+    if M >= 256 and not res_rows:
+        out3 = res[:128].clone()
+        y3 = torch.empty(128, N, device="cuda", dtype=H16)
+        ops.linear(a[:128].contiguous(), w, out3, bias=bias, residual=out3, ln_apply=(gamma, beta, y3, 1e-6))
+        assert torch.equal(y3, y[:128])
