@@ -174,6 +174,14 @@ int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta,
                            float eps, const spg_launch_t* launch);
 
 /*
+ * The same LayerNorm, BIT-IDENTICAL to what a residual GEMM with spg_epilogue_t.ln_apply_* stores for the same rows
+ * (same per-slice sequential statistics, same merge, same normalisation): the host may pick the fused form for large
+ * batches and this kernel in the latency regime without the results depending on the choice.  C in {144, 288, 576}.
+ */
+int spg_layernorm_matched_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
+                                  float eps, const spg_launch_t* launch);
+
+/*
  * im2col for the 7x7 / stride 4 / pad 3 patch embedding: x fp32 NCHW [B,3,S,S] (16-byte aligned) -> cols bf16
  * [B*(S/4)^2, 168], column k = (ky*3 + c)*8 + kx for kx < 7, zero at kx = 7 (each (ky, c) group is one aligned
  * 16-byte gather).  The projection itself is spg_linear_h16 over a weight matrix packed in the same column order, with

@@ -62,10 +62,51 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// Memo of encoded tensor maps (thread-local, direct-mapped): a forward re-encodes the same ~1000 (pointer, shape, box)
+// combinations every call -- workspaces and weights do not move -- and cuTensorMapEncodeTiled costs 1-2 us each.  Pure
+// memoisation of a pure function of its arguments: no effect on results, nothing shared between threads.
+struct TmapKey {
+    const void* base;
+    cuuint64_t dims[5];
+    cuuint64_t strides[4];
+    cuuint32_t box[5];
+    uint32_t rank;
+    int dtype;
+    int swz;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapSlot {
+    TmapKey key;
+    CUtensorMap map;
+    bool valid;
+};
+constexpr int kTmapCacheSlots = 4096;
+
 int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* dims,
            const cuuint64_t* strides, const cuuint32_t* box,
            int dtype = -1 /* -1: the library's 16-bit type, 1: fp32 */,
            CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+    static thread_local TmapSlot* cache = nullptr;
+    if (cache == nullptr) cache = static_cast<TmapSlot*>(calloc(kTmapCacheSlots, sizeof(TmapSlot)));
+    TmapKey key;
+    memset(&key, 0, sizeof(key));
+    key.base = base;
+    key.rank = rank;
+    key.dtype = dtype;
+    key.swz = static_cast<int>(swz);
+    for (uint32_t i = 0; i < rank; ++i) {
+        key.dims[i] = dims[i];
+        key.box[i] = box[i];
+        if (i + 1 < rank) key.strides[i] = strides[i];
+    }
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(&key);
+    for (size_t i = 0; i < sizeof(key); i += 4) h = (h ^ *reinterpret_cast<const uint32_t*>(kb + i)) * 1099511628211ull;
+    TmapSlot* slot = cache != nullptr ? &cache[(h >> 20) & (kTmapCacheSlots - 1)] : nullptr;
+    if (slot != nullptr && slot->valid && slot->key == key) {
+        *out = slot->map;
+        return SPG_OK;
+    }
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(SPG_ERR_INVALID, "TMA operand must be 16-byte aligned");
@@ -76,6 +117,11 @@ int encode(CUtensorMap* out, const void* base, uint32_t rank, const cuuint64_t* 
                     elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(SPG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    if (slot != nullptr) {
+        slot->key = key;
+        slot->map = *out;
+        slot->valid = true;
+    }
     return SPG_OK;
 }
 

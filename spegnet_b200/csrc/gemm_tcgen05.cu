@@ -26,6 +26,7 @@
 
 #include "common.h"
 #include "half16.cuh"
+#include "ln_stats.cuh"
 #include "ptx.cuh"
 
 namespace spg {
@@ -56,7 +57,7 @@ constexpr int kLnBufBytes = 32 * 32;                            // staging buffe
 // exchange area of the per-(n-tile, column slice) row statistics {mean, M2} that the CTAs of a cluster write into each
 // other's shared memory (double-buffered across tiles)
 constexpr int kLnSlots = 2;
-constexpr int kLnMaxParts = 6;
+constexpr int kLnMaxParts = kLnMaxSlices;
 constexpr int kLnXBytes = 2 * kLnMaxParts * kBlockM * 8;
 #ifndef SPG_RES_SLOTS
 #define SPG_RES_SLOTS 3
@@ -605,9 +606,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     uint32_t wb[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float d = v[i] - ln3_shift;  // shifted sums: no cancellation in M2 = s2 - s1^2 / n
-                        ln_s1 += d;
-                        ln_s2 = fmaf(d, d, ln_s2);
+                        ln_accumulate(v[i], ln3_shift, ln_s1, ln_s2);  // shifted sums: no cancellation in M2
                         wb[i] = __float_as_uint(v[i]);
                     }
                     tmem_st16(taddr + c * 16, wb);  // park v over the consumed accumulator columns
@@ -701,9 +700,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const int e = pt == kParts - 1 ? chunks_all : min(chunks_all, p.group * ((units_all * (pt + 1) + kParts - 1) / kParts));
                     return static_cast<float>((e - b) * 16);
                 };
-                const float n_i = static_cast<float>(n_my * 16);
-                const float mean_i = n_my > 0 ? ln3_shift + ln_s1 / n_i : 0.f;
-                const float m2_i = n_my > 0 ? fmaxf(ln_s2 - ln_s1 * ln_s1 / n_i, 0.f) : 0.f;
+                const float2 mine = n_my > 0 ? ln_slice_stats(ln3_shift, ln_s1, ln_s2, static_cast<float>(n_my * 16)) : make_float2(0.f, 0.f);
+                const float mean_i = mine.x, m2_i = mine.y;
                 const uint32_t my_x = ln_x_addr + static_cast<uint32_t>(((ln_buf * kLnMaxParts + n_blk * kParts + part) * kBlockM + row_in_tile) * 8);
                 for (int j = 0; j < p.num_n_tiles; ++j) {
                     const uint32_t peer = kPair ? static_cast<uint32_t>(2 * j) + rank : static_cast<uint32_t>(j);
@@ -717,18 +715,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 mbar_wait_cluster(ln_bar(ln_buf), (ln_phase >> ln_buf) & 1u);
                 ln_phase ^= 1u << ln_buf;
                 const float2* px = ln_x_ptr + (ln_buf * kLnMaxParts) * kBlockM + row_in_tile;
-                const int nparts = p.num_n_tiles * kParts;
-                float mean = 0.f;
-                for (int q = 0; q < nparts; ++q) mean = fmaf(slice_cols(q % kParts), px[q * kBlockM].x, mean);
-                mean *= p.ln_inv_cols;
-                float m2 = 0.f;
-                for (int q = 0; q < nparts; ++q) {
-                    const float2 st = px[q * kBlockM];
-                    const float d = st.x - mean;
-                    m2 += fmaf(slice_cols(q % kParts) * d, d, st.y);
-                }
-                const float rstd = rsqrtf(m2 * p.ln_inv_cols + p.ln_eps);
-                const float mr = -mean * rstd;
+                const float2 rm = ln_merge(p.num_n_tiles * kParts, [&](int q) { return px[q * kBlockM]; },
+                                           [&](int q) { return slice_cols(q % kParts); }, p.ln_inv_cols, p.ln_eps);
                 ln_buf ^= 1;
                 // ---- pass 2: y = (v - mean) * rstd * gamma + beta, 16 bit, staged per 16-column chunk and TMA-stored
                 uint32_t ya[16], yb[16];
@@ -741,10 +729,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int i = 0; i < 4; ++i) {
                         const float4 g = reinterpret_cast<const float4*>(cws + col)[i];
                         const float4 b = reinterpret_cast<const float4*>(lnbs + col)[i];
-                        y[4 * i + 0] = fmaf(fmaf(__uint_as_float(raw[4 * i + 0]), rstd, mr), g.x, b.x);
-                        y[4 * i + 1] = fmaf(fmaf(__uint_as_float(raw[4 * i + 1]), rstd, mr), g.y, b.y);
-                        y[4 * i + 2] = fmaf(fmaf(__uint_as_float(raw[4 * i + 2]), rstd, mr), g.z, b.z);
-                        y[4 * i + 3] = fmaf(fmaf(__uint_as_float(raw[4 * i + 3]), rstd, mr), g.w, b.w);
+                        y[4 * i + 0] = ln_normalise(__uint_as_float(raw[4 * i + 0]), rm, g.x, b.x);
+                        y[4 * i + 1] = ln_normalise(__uint_as_float(raw[4 * i + 1]), rm, g.y, b.y);
+                        y[4 * i + 2] = ln_normalise(__uint_as_float(raw[4 * i + 2]), rm, g.z, b.z);
+                        y[4 * i + 3] = ln_normalise(__uint_as_float(raw[4 * i + 3]), rm, g.w, b.w);
                     }
                     uint8_t* lst = my_ln3_staging_ptr + ln_slot * kLnBufBytes + lane * 32;
                     const uint32_t lx = (lane >> 2) & 1u;  // 32-byte swizzle: the two 16-byte pieces swap on rows 4..7 of 8
@@ -1101,12 +1089,8 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     if (ep != nullptr && ep->ln_apply_out != nullptr) {
         // LayerNorm producer: a FIXED tiling per N (never a function of M: the row statistics are combined per
         // (n-tile, column slice), and results must not depend on the batch size) with at most 3 equal n-tiles
-        a.block_n = 0;
-        for (int bn = 192; bn >= 16; bn -= 16)
-            if (N % bn == 0 && N / bn <= kLnMaxParts / (kEpiWarpsDefault / 4)) {
-                a.block_n = bn;
-                break;
-            }
+        const LnSlices sl = ln_slices_for(N);
+        a.block_n = sl.count > 0 ? 2 * N / sl.count : 0;
         SPG_CHECK_ARG(a.block_n != 0, "ln_apply_out: N=%d has no tiling into <= 3 equal n-tiles of <= 192 columns", N);
     }
     a.num_n_tiles = (N + a.block_n - 1) / a.block_n;

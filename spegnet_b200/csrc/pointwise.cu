@@ -5,6 +5,7 @@
 
 #include "common.h"
 #include "half16.cuh"
+#include "ln_stats.cuh"
 
 namespace spg {
 extern std::atomic<long long> g_launches;
@@ -577,6 +578,61 @@ mask_stats_scalar_kernel(const float* __restrict__ logits, const unsigned char* 
     }
 }
 
+// LayerNorm whose result is BIT-IDENTICAL to what a residual GEMM with spg_epilogue_t.ln_apply_* stores (same slice
+// table, same sequential per-slice sums, same merge and normalisation: ln_stats.cuh).  One warp per row: lane q < count
+// walks slice q of the row in column order straight from global memory (16-byte loads; no shared memory: six lanes on a
+// stride of 96 floats would all hit one bank), the partials are merged by every lane, the normalisation re-reads the
+// row (L1 / L2 hit) coalesced.  Used in the latency regime, where the fused form does not pay: 4.4 us for 1024 rows of
+// 576 channels against 2.7 us for the free-order kernel above (the 96-long dependent chains are the price of matching
+// the GEMM epilogue's summation order; packing several rows into a warp measured slower, 6.4 us: divergent row reads).
+__global__ void __launch_bounds__(128) layernorm_sliced_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, uint16_t* __restrict__ y, int M,
+                                                               int C, float eps, LnSlices sl) {
+    pdl_prologue();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float inv_cols = 1.0f / static_cast<float>(C);
+    int lo = 0, hi = 0;
+#pragma unroll
+    for (int q = 0; q < kLnMaxSlices; ++q)  // static indexing: the table stays in the constant bank
+        if (q == lane && q < sl.count) {
+            lo = sl.bound[q];
+            hi = sl.bound[q + 1];
+        }
+    for (int r = blockIdx.x * 4 + warp; r < M; r += gridDim.x * 4) {
+        const float* xr = x + static_cast<size_t>(r) * C;
+        float2 mine = make_float2(0.f, 0.f);
+        if (hi > lo) {
+            const float4* src = reinterpret_cast<const float4*>(xr + lo);
+            const float shift = __ldg(xr + lo);
+            float s1 = 0.f, s2 = 0.f;
+            for (int j = 0; j < (hi - lo) >> 2; ++j) {
+                const float4 v = __ldg(src + j);
+                ln_accumulate(v.x, shift, s1, s2);
+                ln_accumulate(v.y, shift, s1, s2);
+                ln_accumulate(v.z, shift, s1, s2);
+                ln_accumulate(v.w, shift, s1, s2);
+            }
+            mine = ln_slice_stats(shift, s1, s2, static_cast<float>(hi - lo));
+        }
+        const float2 rm = ln_merge(
+            sl.count,
+            [&](int q) { return make_float2(__shfl_sync(0xffffffffu, mine.x, q), __shfl_sync(0xffffffffu, mine.y, q)); },
+            [&](int q) { return static_cast<float>(__shfl_sync(0xffffffffu, hi - lo, q)); }, inv_cols, eps);
+        uint16_t* yr = y + static_cast<size_t>(r) * C;
+        for (int i = lane * 8; i < C; i += 256) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(xr + i)), a1 = __ldg(reinterpret_cast<const float4*>(xr + i) + 1);
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + i)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + i) + 1);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + i)), b1 = __ldg(reinterpret_cast<const float4*>(beta + i) + 1);
+            float v[8];
+            v[0] = ln_normalise(a0.x, rm, g0.x, b0.x); v[1] = ln_normalise(a0.y, rm, g0.y, b0.y);
+            v[2] = ln_normalise(a0.z, rm, g0.z, b0.z); v[3] = ln_normalise(a0.w, rm, g0.w, b0.w);
+            v[4] = ln_normalise(a1.x, rm, g1.x, b1.x); v[5] = ln_normalise(a1.y, rm, g1.y, b1.y);
+            v[6] = ln_normalise(a1.z, rm, g1.z, b1.z); v[7] = ln_normalise(a1.w, rm, g1.w, b1.w);
+            *reinterpret_cast<uint4*>(yr + i) = pack8(v);
+        }
+    }
+}
+
 inline unsigned blocks_for(long long total, int per_block = 256) {
     return static_cast<unsigned>((total + per_block - 1) / per_block);
 }
@@ -620,6 +676,20 @@ extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const f
         else
             SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 9>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, st.reverse ? 1 : 0)));
     }
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_layernorm_matched_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
+                                             float eps, const spg_launch_t* launch) {
+    SPG_CHECK_ARG(x && gamma && beta && y, "null pointer");
+    SPG_CHECK_ARG(M > 0 && C > 0 && C % 8 == 0, "bad LayerNorm shape M=%d C=%d", M, C);
+    const LnSlices sl = ln_slices_for(C);
+    SPG_CHECK_ARG(sl.count > 0, "C=%d has no producer-side LayerNorm tiling (supported: 144, 288, 576)", C);
+    const LaunchCtx st(launch);
+    const unsigned want = static_cast<unsigned>((M + 3) / 4), cap = static_cast<unsigned>(sm_count()) * 16u;
+    SPG_CHECK_CUDA((launch_pdl(layernorm_sliced_kernel, want < cap ? want : cap, 128, 0, st, x, gamma, beta,
+                               static_cast<uint16_t*>(y), M, C, eps, sl)));
     SPG_LAUNCHED();
     return SPG_OK;
 }

@@ -214,10 +214,17 @@ class SPEGNet(nn.Module):
         # traffic per batch-64 step, but measured 972 vs 981 img/s at batch 64 (the residual GEMMs pay for the second
         # store and the consumers for reading the row records) and 3.00 vs 3.09 ms at batch 1, and the row statistics
         # then depend on the n-tiling, i.e. on the batch size, in the last bit.  Off by default (SPG_LN_FUSE=1 enables).
-        # Default trunk: every residual GEMM whose output feeds a LayerNorm of width 144 / 288 / 576 normalises its own
-        # rows in its epilogue (spg_epilogue_t.ln_apply_*; a cluster of the CTAs holding the row block exchanges row
-        # statistics), so stages 1-3 launch no LayerNorm kernel at all.  SPG_LN_APPLY=0 restores the separate kernels.
-        self.ln_apply = os.environ.get("SPG_LN_APPLY", "1") != "0"
+        # LayerNorm applied by the GEMM that produces its input (spg_epilogue_t.ln_apply_*; the CTAs holding a row block
+        # form a cluster and exchange row statistics over distributed shared memory): widths 144 / 288 / 576.
+        #   1 (default): the second MLP layer (K = 4 d: the two-pass epilogue hides behind the main loop) also emits the
+        #      next block's norm1 -- measured faster than GEMM + LayerNorm kernel by 18 / 38 / 37 us per launch in stages
+        #      3 / 2 / 1 (tools/ln_bench.py);
+        #   2: additionally the attention projection and the patch embedding (K = d: the epilogue is the critical path
+        #      there and the fused form measured 10-12 us SLOWER than the two kernels): no LayerNorm launch in stages 1-3;
+        #   0: every LayerNorm is its own kernel.
+        self.ln_apply = int(os.environ.get("SPG_LN_APPLY", "1"))
+        # below this many rows the same LayerNorm runs as its own (bit-identical) kernel: spg_layernorm_matched_f32_h16
+        self.ln_apply_min_rows = int(os.environ.get("SPG_LN_APPLY_MIN_ROWS", "16384"))
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._ln_fuse = os.environ.get("SPG_LN_FUSE", "0") != "0"
         self._debug_taps: Optional[Dict[str, torch.Tensor]] = None  # tests: stream snapshot after every block
@@ -463,21 +470,25 @@ class SPEGNet(nn.Module):
         G = S // 4
         blocks = self.blocks
         ends = self.spec.stage_ends
-        fused_widths = (144, 288, 576) if self.ln_apply else ()
+        fused_widths = (144, 288, 576)
 
-        def ln_after(width: int, gamma_key: str, rows: int):
-            """(ln_apply tuple for the producing GEMM, y) when the LayerNorm `gamma_key` over `width` channels is applied
-            by its producer; (None, y) when a separate LayerNorm launch has to follow."""
+        def ln_after(width: int, gamma_key: str, rows: int, long_k: bool):
+            """How the LayerNorm `gamma_key` over `width` channels of a residual GEMM's output is computed: returns
+            (ln_apply tuple or None, y, kernel).  With a tuple the producing GEMM stores y itself; otherwise `kernel` has
+            to be launched on the fp32 stream afterwards.  For the widths the producers support, the separate kernel is
+            the bit-identical `layernorm_matched`, so the choice (large batches: fused; latency regime: separate, the
+            two-pass epilogue and the cluster launch cost ~5 us per GEMM there) never changes a result."""
             y = ws.y[: rows * width].view(rows, width)
-            if width in fused_widths:
-                return (W[gamma_key + ".w"], W[gamma_key + ".b"], y, LN_EPS), y
-            return None, y
+            if width in fused_widths and self.ln_apply >= (1 if long_k else 2):
+                if rows >= self.ln_apply_min_rows:
+                    return (W[gamma_key + ".w"], W[gamma_key + ".b"], y, LN_EPS), y, None
+                return None, y, ops.layernorm_matched
+            return None, y, ops.layernorm
 
         ops.patchify(x, ws.cols)
         # the patch embedding (+ positional embedding as a broadcast residual) feeds block 0's norm1
-        ap, y = ln_after(blocks[0].dim_in, "b0.n1", B * G * G)
+        ap, y, ln1 = ln_after(blocks[0].dim_in, "b0.n1", B * G * G, False)
         ops.linear(ws.cols, W["pe.w"], ws.x[0], bias=W["pe.b"], residual=ws.pos, res_rows=G * G, ln_apply=ap)
-        y_ready = ap is not None
         H = G
         cur = ws.x[0]
         if self._debug_taps is not None:
@@ -486,8 +497,8 @@ class SPEGNet(nn.Module):
             p = f"b{b.index}."
             M = B * H * H
             y = ws.y[: M * b.dim_in].view(M, b.dim_in)
-            if not y_ready:
-                ops.layernorm(cur, W[p + "n1.w"], W[p + "n1.b"], y, LN_EPS)
+            if ln1 is not None:
+                ln1(cur, W[p + "n1.w"], W[p + "n1.b"], y, LN_EPS)
             if b.dim_in != b.dim_out:
                 if not b.q_pool:
                     raise NotImplementedError("channel change without query pooling does not occur in Hiera-L")
@@ -504,18 +515,17 @@ class SPEGNet(nn.Module):
             att = ws.att[: Mo * b.dim_out].view(Mo, b.dim_out)
             ops.window_attention(qkv, att, B, H, H, b.dim_out, b.heads, b.window, b.q_pool)
             # attention projection + residual; its output feeds norm2
-            ap, z = ln_after(b.dim_out, p + "n2", Mo)
+            ap, z, ln2 = ln_after(b.dim_out, p + "n2", Mo, False)
             ops.linear(att, W[p + "ap.w"], nxt, bias=W[p + "ap.b"], residual=nxt, ln_apply=ap)
-            if ap is None:
-                ops.layernorm(nxt, W[p + "n2.w"], W[p + "n2.b"], z, LN_EPS)
+            if ln2 is not None:
+                ln2(nxt, W[p + "n2.w"], W[p + "n2.b"], z, LN_EPS)
             hid = ws.hid[: Mo * 4 * b.dim_out].view(Mo, 4 * b.dim_out)
             ops.linear(z, W[p + "fc1.w"], hid, bias=W[p + "fc1.b"], act=ops.ACT_GELU)
             # second MLP layer + residual; its output feeds the NEXT block's norm1 (nothing after the last block)
-            ap = None
+            ap, ln1 = None, None
             if bi + 1 < len(blocks):
-                ap, _ = ln_after(b.dim_out, f"b{blocks[bi + 1].index}.n1", Mo)
+                ap, _, ln1 = ln_after(b.dim_out, f"b{blocks[bi + 1].index}.n1", Mo, True)
             ops.linear(hid, W[p + "fc2.w"], nxt, bias=W[p + "fc2.b"], residual=nxt, ln_apply=ap)
-            y_ready = ap is not None
             cur, H = nxt, Ho
             if self._debug_taps is not None:
                 self._debug_taps[f"block{b.index}"] = cur.view(B, H, H, b.dim_out).clone()

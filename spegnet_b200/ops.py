@@ -183,6 +183,15 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch
     _lib.check(rc, "spg_layernorm_f32_h16", dn)
 
 
+def layernorm_matched(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, y: torch.Tensor, eps: float) -> None:
+    """LayerNorm bit-identical to `linear(..., ln_apply=...)` on the same rows (spg_layernorm_matched_f32_h16)."""
+    M, Cc = x.shape
+    lib, dn = _lib_for(y)
+    rc = lib.spg_layernorm_matched_f32_h16(_ptr(x, torch.float32, "x"), _ptr(gamma, torch.float32, "gamma"),
+                                           _ptr(beta, torch.float32, "beta"), _ptr(y, H16, "y"), M, Cc, eps, _launch(True))
+    _lib.check(rc, "spg_layernorm_matched_f32_h16", dn)
+
+
 def patchify(x: torch.Tensor, cols: torch.Tensor) -> None:
     B, _, S, _ = x.shape
     lib, dn = _lib_for(cols)

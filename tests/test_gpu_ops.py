@@ -440,3 +440,23 @@ def test_layernorm_applied_by_the_producer(ops, M, N, K, res_rows):
         y3 = torch.empty(128, N, device="cuda", dtype=H16)
         ops.linear(a[:128].contiguous(), w, out3, bias=bias, residual=out3, ln_apply=(gamma, beta, y3, 1e-6))
         assert torch.equal(y3, y[:128])
+
+
+@pytest.mark.parametrize("C", [144, 288, 576])
+def test_matched_layernorm_is_bit_identical_to_the_producer(ops, C):
+    """spg_layernorm_matched_f32_h16 on the fp32 stream == the y a residual GEMM stores with ln_apply, bit for bit (the
+    host switches between the two by batch size)."""
+    M, K = 1000, 4 * C
+    g = torch.Generator(device="cuda").manual_seed(C)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(C, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(C, device="cuda", generator=g)
+    out = torch.randn(M, C, device="cuda", generator=g) * 3 + 0.3
+    gamma = torch.rand(C, device="cuda", generator=g) + 0.5
+    beta = torch.randn(C, device="cuda", generator=g)
+    y = torch.empty(M, C, device="cuda", dtype=H16)
+    ops.linear(a, w, out, bias=bias, residual=out, ln_apply=(gamma, beta, y, 1e-6))
+    y2 = torch.empty_like(y)
+    ops.layernorm_matched(out, gamma, beta, y2, 1e-6)
+    assert torch.equal(y, y2)
+    _close(y2, F.layer_norm(out, (C,), gamma, beta, 1e-6), 2e-2, 1e-2)
