@@ -112,3 +112,28 @@ def test_predict_single_matches_oracle_pipeline(ops, spread_sd):
     assert float((edge.cpu() - want_edge).abs().max()) <= 1e-2
     mask = predict.binary_mask_u8(seg)
     assert mask.dtype == torch.uint8 and int((mask.cpu().int() - (want_seg * 255).to(torch.uint8).int()).abs().max()) <= 3
+
+
+def test_collate_decoded_ragged_batch_matches_the_reference_path():
+    """Ragged decoded images + ragged masks -> one device batch: every slot equals the oracle's process_image of that
+    image, masks are the reference's (mask > 127.5).float() at their own sizes, and the evaluator scoring loop accepts
+    the result as is."""
+    import numpy as np
+
+    from oracle.preprocess import process_image_array
+    from spegnet_b200.batching import collate_decoded
+
+    rng = np.random.RandomState(3)
+    sizes = [(300, 400), (512, 512), (641, 333)]
+    imgs = [rng.randint(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    masks = [rng.randint(0, 256, (h, w), dtype=np.uint8) for h, w in sizes]
+    out = collate_decoded([torch.from_numpy(a).cuda() for a in imgs], [torch.from_numpy(m).cuda() for m in masks],
+                          names=["a", "b", "c"], target_size=256)
+    assert tuple(out["images"].shape) == (3, 3, 256, 256) and out["names"] == ["a", "b", "c"]
+    for i, a in enumerate(imgs):
+        want = process_image_array(a, 256)
+        assert float((out["images"][i].cpu() - want).abs().max()) <= 2e-5
+        ref_mask = (torch.from_numpy(masks[i]).float() > 127.5).float()[None]
+        assert torch.equal(out["masks"][i].cpu(), ref_mask)
+    with pytest.raises(ValueError):
+        collate_decoded([])

@@ -460,3 +460,66 @@ def test_matched_layernorm_is_bit_identical_to_the_producer(ops, C):
     ops.layernorm_matched(out, gamma, beta, y2, 1e-6)
     assert torch.equal(y, y2)
     _close(y2, F.layer_norm(out, (C,), gamma, beta, 1e-6), 2e-2, 1e-2)
+
+
+class _Guarded:
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_unavailable.txt), so out-of-bounds WRITES are
+    caught the manual way: every output lives between two guard bands filled with a sentinel bit pattern."""
+
+    GUARD = 4096  # elements on each side
+
+    def __init__(self, shape, dtype):
+        n = 1
+        for s in shape:
+            n *= s
+        self.flat = torch.empty(n + 2 * self.GUARD, dtype=dtype, device="cuda")
+        self.sentinel = -7.0 if dtype.is_floating_point else 171
+        self.flat.fill_(self.sentinel)
+        self.view = self.flat[self.GUARD:self.GUARD + n].view(*shape)
+
+    def intact(self):
+        lo, hi = self.flat[:self.GUARD], self.flat[-self.GUARD:]
+        return bool((lo == self.sentinel).all()) and bool((hi == self.sentinel).all())
+
+
+def test_no_writes_outside_the_outputs(ops):
+    g = torch.Generator(device="cuda").manual_seed(99)
+    # GEMM with ragged M / N tails, fp32 residual, 16-bit and fp32 outputs, producer-side LayerNorm (16-bit second output)
+    for M, N, K in [(300, 192, 128), (1000, 576, 576), (129, 144, 168), (2000, 1728, 576)]:
+        a = _bf(torch.randn(M, K, device="cuda", generator=g))
+        w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+        out = _Guarded((M, N), H16)
+        ops.linear(a, w, out.view, bias=torch.randn(N, device="cuda", generator=g), act=ops.ACT_GELU)
+        assert out.intact(), ("linear h16", M, N, K)
+        outf = _Guarded((M, N), torch.float32)
+        outf.view.normal_(generator=g)
+        if N in (144, 576):
+            y = _Guarded((M, N), H16)
+            ops.linear(a, w, outf.view, residual=outf.view, ln_apply=(torch.ones(N, device="cuda"), torch.zeros(N, device="cuda"), y.view, 1e-6))
+            assert y.intact() and bool(torch.isfinite(y.view.float()).all()), ("ln_apply", M, N, K)
+            y2 = _Guarded((M, N), H16)
+            ops.layernorm_matched(outf.view, torch.ones(N, device="cuda"), torch.zeros(N, device="cuda"), y2.view, 1e-6)
+            assert y2.intact() and torch.equal(y2.view, y.view)
+        else:
+            ops.linear(a, w, outf.view, residual=outf.view)
+        assert outf.intact(), ("linear f32", M, N, K)
+    # implicit-GEMM conv with fused head, fused up2 conv
+    x = _bf(torch.randn(1, 64, 64, 64, device="cuda", generator=g))
+    wk = _bf(torch.randn(64, 9 * 64, device="cuda", generator=g) / 24)
+    out = _Guarded((64 * 64, 64), H16)
+    head = _Guarded((1, 1, 64, 64), torch.float32)
+    ops.conv3x3(x, wk, out.view, bias=torch.zeros(64, device="cuda"), act=ops.ACT_RELU, head_w=torch.ones(64, device="cuda"), head_out=head.view)
+    assert out.intact() and head.intact()
+    # LayerNorm, attention (windowed tcgen05, small windows, pooled queries), max pool, cast
+    xs = torch.randn(1000, 576, device="cuda", generator=g)
+    y = _Guarded((1000, 576), H16)
+    ops.layernorm(xs, torch.ones(576, device="cuda"), torch.zeros(576, device="cuda"), y.view, 1e-6)
+    assert y.intact()
+    for (B, Hh, D, heads, win, pool) in [(1, 32, 576, 8, 16, False), (1, 32, 144, 2, 8, False), (2, 16, 288, 4, 8, True), (1, 16, 288, 4, 4, False),
+                                         (1, 32, 576, 8, 0, False)]:
+        qkv = _bf(torch.randn(B * Hh * Hh, 3 * D, device="cuda", generator=g))
+        Ho = Hh // 2 if pool else Hh
+        o = _Guarded((B * Ho * Ho, D), H16)
+        ops.window_attention(qkv, o.view, B, Hh, Hh, D, heads, win, pool)
+        assert o.intact() and bool(torch.isfinite(o.view.float()).all()), (B, Hh, D, heads, win, pool)
+    torch.cuda.synchronize()

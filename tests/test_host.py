@@ -148,3 +148,21 @@ def test_up2_phase_weights_reproduce_interpolate_then_conv():
             out[:, y, col] += a @ dW.t()
     got = out.reshape(B, H, W, 2, 2, Co).permute(0, 5, 1, 3, 2, 4).reshape(B, Co, 2 * H, 2 * W)
     assert float((got - ref).abs().max()) < 1e-12
+
+
+def test_collate_fn_mirrors_the_reference():
+    """utils/data_loader.py:177-212: stacked images, ragged masks kept as a list, 'names' for test samples / 'edges' for
+    training samples, ValueError on an empty batch."""
+    import torch
+
+    from spegnet_b200.batching import collate_fn
+
+    items = [{"image": torch.zeros(3, 8, 8) + i, "mask": torch.ones(1, 5 + i, 7), "name": f"img{i}.png"} for i in range(3)]
+    out = collate_fn(items)
+    assert tuple(out["images"].shape) == (3, 3, 8, 8) and float(out["images"][2].mean()) == 2.0
+    assert [tuple(m.shape) for m in out["masks"]] == [(1, 5, 7), (1, 6, 7), (1, 7, 7)]
+    assert out["names"] == ["img0.png", "img1.png", "img2.png"] and "edges" not in out
+    train = collate_fn([dict(it, edge=torch.zeros(1, 4, 4)) for it in items])
+    assert len(train["edges"]) == 3 and "names" not in train
+    with pytest.raises(ValueError, match="Empty batch"):
+        collate_fn([])
