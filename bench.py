@@ -29,13 +29,13 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 GFLOP_PER_IMAGE = {512: 610.98, 1024: 2530.89}  # algorithmic, reference formulation
-# DRAM traffic of one launch of the dominant kernel from an `ncu --set full` capture (profiles/
-# r01_gemm_qkv_ncu_full_summary.txt): the stage-3 QKV GEMM at batch 64 (M=65536, N=1728, K=576),
-# dram__bytes_read.sum 77.6 MB (algorithmic 77.5 MB: every operand byte is read exactly once) +
-# dram__bytes_write.sum 173.9 MB (algorithmic 226.5 MB; the remainder is still in the 126 MB L2 at kernel end).
-NCU_TRAFFIC = {"bytes_per_launch": 77_608_192 + 173_853_952, "launch": "stage-3 QKV GEMM, M=65536 N=1728 K=576",
-               "algorithmic_bytes": 65536 * 576 * 2 + 1728 * 576 * 2 + 65536 * 1728 * 2,
-               "source": "profiles/r01_gemm_qkv_ncu_full_summary.txt"}
+# DRAM traffic of one launch of the dominant kernel from an `ncu --set full` capture inside the real batch-64 step
+# (profiles/r02_gemm_ncu_summary.md): the stage-3 fc1 + GELU GEMM (M=65536, N=2304, K=576), the instance with the
+# largest share of the step: dram__bytes_read.sum 78.2 MB (algorithmic 78.2 MB: every operand byte is read exactly
+# once) + dram__bytes_write.sum 249.5 MB (algorithmic 302.0 MB; the remainder is still in the 126 MB L2 at kernel end).
+NCU_TRAFFIC = {"bytes_per_launch": 78_191_872 + 249_466_624, "launch": "stage-3 fc1 + GELU GEMM, M=65536 N=2304 K=576",
+               "algorithmic_bytes": 65536 * 576 * 2 + 2304 * 576 * 2 + 65536 * 2304 * 2,
+               "source": "profiles/r02_gemm_ncu_summary.md"}
 FALLBACK_PEAKS = {"bf16_tflops_sustained": 1400.0, "bf16_tflops": 1590.0, "hbm_gbs": 6650.0}
 # What each storage type is good for (DESIGN.md "Numerics", profiles/r02_precision_budget.md): masks vs the fp32
 # reference on the seed-0 spread fixture, max |delta sigmoid|; the north-star bar is 1e-2.
