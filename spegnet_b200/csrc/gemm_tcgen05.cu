@@ -76,6 +76,10 @@ struct GemmArgs {
     int l2_prefetch; // linear mode: prefetch the next tile's A rows into L2 one tile ahead
     int pair;        // launch as CTA pairs (cta_group::2): decided on the host, selects the kPair kernel instance
     int halo;        // conv only: one stage = a 130-pixel halo row of A + the 3 dx-tap weight tiles (A reuse x3)
+    // linear, short K (<= 3 k-chunks): the CTA's weight tile stays RESIDENT in shared memory (the grid is a multiple of
+    // the n-tiles, so a CTA keeps one n-block for all its tiles) and the ring holds A chunks only: 2-3 tiles in flight
+    // per TMA round trip instead of 1.3 -- these GEMMs are bound by that round trip, not by the tensor pipe
+    int b_resident;
     // conv mode
     int conv;
     int H, W, cin_chunks, tile_w;
@@ -175,13 +179,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t b_stage_bytes = static_cast<uint32_t>(kPair ? p.block_n / 2 : p.block_n) * 128u;
     // halo mode: A stage = 130 pixels x 128 B (padded to 17 KB so stages stay 1 KB aligned) + three weight tiles
     const uint32_t a_stage_bytes = p.halo ? kHaloABytes : kAStageBytes;
-    const uint32_t stage_bytes = a_stage_bytes + (p.halo ? 3u : 1u) * b_stage_bytes;
-    const uint32_t bar_addr = tiles_addr + static_cast<uint32_t>(p.stages) * stage_bytes;
+    const uint32_t stage_bytes = a_stage_bytes + (p.b_resident ? 0u : (p.halo ? 3u : 1u) * b_stage_bytes);
+    const uint32_t b_res_addr = tiles_addr + static_cast<uint32_t>(p.stages) * stage_bytes;  // resident weight tile (b_resident)
+    const uint32_t bar_addr = b_res_addr + (p.b_resident ? static_cast<uint32_t>(p.num_k_chunks) * b_stage_bytes : 0u);
     auto full_bar = [&](int s) { return bar_addr + 8u * s; };
     auto empty_bar = [&](int s) { return bar_addr + 8u * (p.stages + s); };
     auto tmem_full_bar = [&](int a) { return bar_addr + 8u * (2 * p.stages + a); };
     auto tmem_empty_bar = [&](int a) { return bar_addr + 8u * (2 * p.stages + 2 + a); };
     const uint32_t tmem_slot = bar_addr + 8u * (2 * p.stages + 4);
+    const uint32_t b_res_bar = bar_addr + 8u * (2 * p.stages + 5);  // the resident weight tile has landed
     auto res_bar = [&](int ew, int slot) { return bar_addr + 256u + 8u * (ew * kResSlots + slot); };
     auto ln_bar = [&](int b) { return bar_addr + 768u + 8u * b; };  // kLn == 3: statistics of tile parity b have arrived
     const uint32_t scratch_addr = bar_addr + kBarBytes;
@@ -204,6 +210,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
+        mbar_init(b_res_bar, 1);
         for (int a = 0; a < 2; ++a) {
             mbar_init(tmem_full_bar(a), 1);
             mbar_init(tmem_empty_bar(a), kPair ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (both CTAs)
@@ -241,6 +248,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // pair mode: both CTAs load; all transaction bytes are signalled on the leader's full barrier
             const uint32_t n_half = kPair ? rank * (p.block_n / 2) : 0u;  // this CTA's slice of the weight tile
             [[maybe_unused]] int trace_i = 0;
+            if (p.b_resident && unit < total_tiles) {
+                // this CTA's n-block never changes (grid % n-tiles == 0): load its weight tile once
+                const int t0 = p.reverse ? total_tiles - 1 - unit : unit;
+                const int n_fixed = t0 % p.num_n_tiles;
+                mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(p.num_k_chunks) * b_stage_bytes);
+                for (int kc = 0; kc < p.num_k_chunks; ++kc)
+                    tma_load_2d(b_res_addr + kc * b_stage_bytes, &tmap_b, b_res_bar, kc * kBlockK, n_fixed * p.block_n);
+            }
             for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
                 SPG_STAMP(trace_i, 0);
                 const int t_idx = p.reverse ? total_tiles - 1 - tile : tile;
@@ -298,6 +313,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                         continue;
                     }
+                    if (p.b_resident) {  // A chunk only; the weights are resident
+                        mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+                        tma_load_2d(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
+                        if (++stage == p.stages) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                        continue;
+                    }
                     if (leader) mbar_arrive_expect_tx(full_bar(stage), kPair ? 2u * stage_bytes : stage_bytes);
                     if (p.conv) {
                         const int tap = kc / p.cin_chunks;
@@ -337,6 +361,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int acc = 0;
             uint32_t acc_phase = 0;
             [[maybe_unused]] int trace_i = 0;
+            if (p.b_resident && unit < total_tiles) {
+                mbar_wait(b_res_bar, 0);
+                tc_fence_after();
+            }
             for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
                 SPG_STAMP(trace_i, 2);
                 mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
@@ -374,7 +402,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         }
                     } else {
                         const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-                        const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kAStageBytes);
+                        const uint64_t b_desc = make_sw128_kmajor_desc(p.b_resident ? b_res_addr + kc * b_stage_bytes : a_addr + kAStageBytes);
                         // K tail (K = 144 / 288 / 168 in stages 1-2 and the patch embedding): the zero-filled k-steps of
                         // the last chunk are not issued at all (25 % / 10 % of those GEMMs' tensor work)
                         const int ksteps = kc == p.num_k_chunks - 1 ? p.last_chunk_ksteps : kBlockK / kUmmaK;
@@ -855,14 +883,15 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     const bool pair = a.pair != 0;
     a.reverse = ctx.reverse ? 1 : 0;
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
-    const int stage_bytes = a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128;
+    const int b_res_bytes = a.b_resident ? a.num_k_chunks * bn_cta * 128 : 0;
+    const int stage_bytes = a.b_resident ? kAStageBytes : (a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128);
     const int staging = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
                         (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0) +
                         (a.ln_mode == 3 ? a.epi_warps * kLnSlots * kLnBufBytes + kLnXBytes : 0);
-    const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging;
+    const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging + b_res_bytes;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
-    if (stages > a.num_k_chunks + 1) stages = a.num_k_chunks + 1;  // no point in a deeper ring
+    if (!a.b_resident && stages > a.num_k_chunks + 1) stages = a.num_k_chunks + 1;  // no point in a deeper ring
     if (stages < 2) stages = 2;
     a.stages = stages;
     const int smem = stages * stage_bytes + fixed;
@@ -877,6 +906,10 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
         grid = total_1cta < sms ? total_1cta : sms;
     }
     grid -= grid % cluster;  // whole clusters only (total tiles are a multiple of the n-tiles per row block)
+    if (a.b_resident) {
+        grid -= grid % a.num_n_tiles;  // a CTA keeps one n-block for all its tiles
+        if (grid == 0) return fail(SPG_ERR_INVALID, "resident-weight mode needs at least one CTA per n-tile");
+    }
     const bool head = a.head_w != nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -1102,6 +1135,10 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.tile_w = 1;
     if (int rc = fill_epilogue(a, em, ep, M, N)) return rc;
     decide_pair(a);
+    // resident weights: short K, plain tiling (N a multiple of block_n), enough tiles that the ring depth matters
+    static const int bres_env = [] { const char* e = getenv("SPG_GEMM_BRES"); return e ? atoi(e) : 1; }();
+    a.b_resident = (bres_env && !a.pair && a.num_k_chunks <= 3 && N % a.block_n == 0 && a.num_n_tiles <= 16 &&
+                    a.num_m_tiles * a.num_n_tiles >= 4 * sm_count() && a.ln_mode != 1 && a.ln_mode != 2) ? 1 : 0;
     static const int l2pf_env = [] { const char* e = getenv("SPG_GEMM_L2PF"); return e ? atoi(e) : 1; }();
     // pays on short reductions without a residual stream (fc1 +3.5 %, QKV +2 %); with K = 2304 and an fp32 residual
     // in flight the extra requests cost 9 %

@@ -523,3 +523,23 @@ def test_no_writes_outside_the_outputs(ops):
         ops.window_attention(qkv, o.view, B, Hh, Hh, D, heads, win, pool)
         assert o.intact() and bool(torch.isfinite(o.view.float()).all()), (B, Hh, D, heads, win, pool)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K,act", [(40000, 432, 144, 0), (30001, 576, 144, 2), (80000, 144, 168, 0), (33000, 864, 144, 0),
+                                       (26000, 288, 144, 0)])
+def test_linear_resident_weights(ops, M, N, K, act):
+    """Short-K GEMMs with many tiles run in the resident-weight mode (the CTA's weight tile is loaded once, the ring
+    holds A chunks only, grid = a multiple of the n-tiles): ragged M, K tails (144 = 2*64 + 16), GELU, fp32 output."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = _bf(torch.randn(M, K, device="cuda", generator=g))
+    w = _bf(torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ w.float().t() + bias
+    if act == 2:
+        ref = F.gelu(ref)
+    out = torch.empty(M, N, device="cuda", dtype=H16)
+    ops.linear(a, w, out, bias=bias, act=act)
+    _close(out, ref, 2e-2, 1e-2)
+    outf = torch.empty(M, N, device="cuda")
+    ops.linear(a, w, outf, bias=bias, act=act)
+    _close(outf, ref, 3e-4, 1e-4)
