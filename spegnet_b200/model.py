@@ -225,6 +225,7 @@ class SPEGNet(nn.Module):
         self.ln_apply = int(os.environ.get("SPG_LN_APPLY", "1"))
         # below this many rows the same LayerNorm runs as its own (bit-identical) kernel: spg_layernorm_matched_f32_h16
         self.ln_apply_min_rows = int(os.environ.get("SPG_LN_APPLY_MIN_ROWS", "16384"))
+        self.ln_apply_widths = tuple(int(v) for v in os.environ.get("SPG_LN_APPLY_WIDTHS", "144,288,576").replace("+", ",").split(",") if v)
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._ln_fuse = os.environ.get("SPG_LN_FUSE", "0") != "0"
         self._debug_taps: Optional[Dict[str, torch.Tensor]] = None  # tests: stream snapshot after every block
@@ -470,7 +471,7 @@ class SPEGNet(nn.Module):
         G = S // 4
         blocks = self.blocks
         ends = self.spec.stage_ends
-        fused_widths = (144, 288, 576)
+        fused_widths = self.ln_apply_widths
 
         def ln_after(width: int, gamma_key: str, rows: int, long_k: bool):
             """How the LayerNorm `gamma_key` over `width` channels of a residual GEMM's output is computed: returns
