@@ -10,7 +10,7 @@ for rep in 1 2; do
 import json
 try:
     d=json.loads(open("gpurun_out/ab_${name}_${rep}.json").read().strip().splitlines()[-1])
-    print("${name} rep${rep}: %.1f img/s  %.3f ms  gemm %.0f TF/s  clk %s" % (d["value"], d["ms_per_step"], d["roofline"]["achieved"], d["clocks"]["sm_mhz"]))
+    print("${name} rep${rep}: %.1f img/s  %.3f ms  e2e %.1f  gemm %.0f TF/s  clk %s" % (d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["achieved"], d["clocks"]["sm_mhz"]))
 except Exception as e:
     print("${name} rep${rep}: ERR", e)
 PY
