@@ -224,7 +224,7 @@ class SPEGNet(nn.Module):
         #   0: every LayerNorm is its own kernel.
         self.ln_apply = int(os.environ.get("SPG_LN_APPLY", "1"))
         # below this many rows the same LayerNorm runs as its own (bit-identical) kernel: spg_layernorm_matched_f32_h16
-        self.ln_apply_min_rows = int(os.environ.get("SPG_LN_APPLY_MIN_ROWS", "16384"))
+        self.ln_apply_min_rows = int(os.environ.get("SPG_LN_APPLY_MIN_ROWS", "4096"))
         self.ln_apply_widths = tuple(int(v) for v in os.environ.get("SPG_LN_APPLY_WIDTHS", "144,288,576").replace("+", ",").split(",") if v)
         self._packed: Optional[Dict[str, torch.Tensor]] = None
         self._ln_fuse = os.environ.get("SPG_LN_FUSE", "0") != "0"
