@@ -390,6 +390,8 @@ def measure(model, args, B: int, S: int, dev, dist, rank: int, world: int, steps
         t0.record()
         for i in range(steps):
             step(i)
+        tc = torch.cuda.Event(enable_timing=True)
+        tc.record()  # this rank's own work is done here; the gather below waits for the slowest rank
         gather_partials()
         t1.record()
         torch.cuda.synchronize()
@@ -401,11 +403,12 @@ def measure(model, args, B: int, S: int, dev, dist, rank: int, world: int, steps
         elapsed_ms = t0.elapsed_time(t1)
         res["rank_ms_per_step"] = elapsed_ms / steps
         if dist is not None:
-            tmax = torch.tensor([elapsed_ms], device=dev)
-            tall = torch.empty(world, device=dev)
+            tmax = torch.tensor([elapsed_ms, t0.elapsed_time(tc)], device=dev)
+            tall = torch.empty(world, 2, device=dev)
             dist.all_gather_into_tensor(tall, tmax)
-            res["per_rank_ms_per_step"] = [round(float(v) / steps, 3) for v in tall.tolist()]
-            elapsed_ms = float(tall.max().item())
+            # own compute time of every rank (before the end-of-run gather): shows which GPU paces the job
+            res["per_rank_ms_per_step"] = [round(float(v) / steps, 3) for v in tall[:, 1].tolist()]
+            elapsed_ms = float(tall[:, 0].max().item())
         res["elapsed_ms"] = elapsed_ms
         res["gemm_ms"] = sum(e0.elapsed_time(e1) for e0, e1, _ in gemm_events)
         res["gemm_flops"] = sum(f for _, _, f in gemm_events)
