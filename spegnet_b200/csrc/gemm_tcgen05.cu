@@ -80,6 +80,7 @@ struct GemmArgs {
     // the n-tiles, so a CTA keeps one n-block for all its tiles) and the ring holds A chunks only: 2-3 tiles in flight
     // per TMA round trip instead of 1.3 -- these GEMMs are bound by that round trip, not by the tensor pipe
     int b_resident;
+    int b_res_tiles;  // weight tiles held resident: k-chunks (linear) or 9 taps x channel chunks (row-halo conv)
     // conv mode
     int conv;
     int H, W, cin_chunks, tile_w;
@@ -181,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const uint32_t a_stage_bytes = p.halo ? kHaloABytes : kAStageBytes;
     const uint32_t stage_bytes = a_stage_bytes + (p.b_resident ? 0u : (p.halo ? 3u : 1u) * b_stage_bytes);
     const uint32_t b_res_addr = tiles_addr + static_cast<uint32_t>(p.stages) * stage_bytes;  // resident weight tile (b_resident)
-    const uint32_t bar_addr = b_res_addr + (p.b_resident ? static_cast<uint32_t>(p.num_k_chunks) * b_stage_bytes : 0u);
+    const uint32_t bar_addr = b_res_addr + (p.b_resident ? static_cast<uint32_t>(p.b_res_tiles) * b_stage_bytes : 0u);
     auto full_bar = [&](int s) { return bar_addr + 8u * s; };
     auto empty_bar = [&](int s) { return bar_addr + 8u * (p.stages + s); };
     auto tmem_full_bar = [&](int a) { return bar_addr + 8u * (2 * p.stages + a); };
@@ -252,8 +253,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 // this CTA's n-block never changes (grid % n-tiles == 0): load its weight tile once
                 const int t0 = p.reverse ? total_tiles - 1 - unit : unit;
                 const int n_fixed = t0 % p.num_n_tiles;
-                mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(p.num_k_chunks) * b_stage_bytes);
-                for (int kc = 0; kc < p.num_k_chunks; ++kc)
+                // (linear: tile kc = k-chunk kc; row-halo conv: tile (tap, cc) = columns ((tap * cin_chunks + cc) * 64 ..) of w)
+                mbar_arrive_expect_tx(b_res_bar, static_cast<uint32_t>(p.b_res_tiles) * b_stage_bytes);
+                for (int kc = 0; kc < p.b_res_tiles; ++kc)
                     tma_load_2d(b_res_addr + kc * b_stage_bytes, &tmap_b, b_res_bar, kc * kBlockK, n_fixed * p.block_n);
             }
             for (int tile = unit; tile < total_tiles; tile += nunits, ++trace_i) {
@@ -296,12 +298,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         // k-chunk = (dy, 64-channel chunk): one 130-pixel halo row serves the taps dx = -1, 0, +1
                         const int dyi = kc / p.cin_chunks;
                         const int cc = kc - dyi * p.cin_chunks;
-                        const uint32_t bytes = 130u * 128u + 3u * b_stage_bytes;
+                        const uint32_t bytes = 130u * 128u + (p.b_resident ? 0u : 3u * b_stage_bytes);
                         if (leader) mbar_arrive_expect_tx(full_bar(stage), kPair ? 2u * bytes : bytes);
                         if (kPair) tma_load_4d_pair(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 - 1, y0 + dyi - 1, img);
                         else tma_load_4d(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 - 1, y0 + dyi - 1, img);
 #pragma unroll
                         for (int dxi = 0; dxi < 3; ++dxi) {
+                            if (p.b_resident) break;  // the nine tap tiles are resident
                             const int kcol = ((dyi * 3 + dxi) * p.cin_chunks + cc) * kBlockK;
                             const int nrow = w_row0 + n_blk * p.block_n + n_half;
                             if (kPair) tma_load_2d_pair(b_dst + dxi * b_stage_bytes, &tmap_b, full_bar(stage), kcol, nrow);
@@ -393,7 +396,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                         for (int dxi = 0; dxi < 3; ++dxi) {
                             const uint64_t a_desc = make_sw128_kmajor_desc(a_addr + dxi * 128u);
-                            const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + a_stage_bytes + dxi * b_stage_bytes);
+                            // k-chunk kc = (dy, channel chunk): tap (dy, dx) of chunk cc is resident tile (dy*3 + dx) * cin_chunks + cc
+                            const int dyi = kc / p.cin_chunks;
+                            const uint64_t b_desc = make_sw128_kmajor_desc(
+                                p.b_resident ? b_res_addr + static_cast<uint32_t>((dyi * 3 + dxi) * p.cin_chunks + (kc - dyi * p.cin_chunks)) * b_stage_bytes
+                                             : a_addr + a_stage_bytes + dxi * b_stage_bytes);
 #pragma unroll
                             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                                 const uint64_t koff = static_cast<uint64_t>((k * kUmmaK * 2) >> 4);
@@ -883,8 +890,10 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     const bool pair = a.pair != 0;
     a.reverse = ctx.reverse ? 1 : 0;
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
-    const int b_res_bytes = a.b_resident ? a.num_k_chunks * bn_cta * 128 : 0;
-    const int stage_bytes = a.b_resident ? kAStageBytes : (a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128);
+    a.b_res_tiles = a.b_resident ? (a.halo ? 9 * a.cin_chunks : a.num_k_chunks) : 0;
+    const int b_res_bytes = a.b_res_tiles * bn_cta * 128;
+    const int stage_bytes = a.b_resident ? (a.halo ? kHaloABytes : kAStageBytes)
+                                         : (a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128);
     const int staging = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
                         (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0) +
                         (a.ln_mode == 3 ? a.epi_warps * kLnSlots * kLnBufBytes + kLnXBytes : 0);
@@ -1181,6 +1190,11 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     if (a.halo) a.num_k_chunks = 3 * a.cin_chunks;
     if (int rc = fill_epilogue(a, em, ep, a.M, Cout)) return rc;
     decide_pair(a);
+    // narrow row-halo convs whose nine tap tiles fit next to a deep A ring keep the weights resident (Cout = 64,
+    // Cin = 64: 72 KB): no weight refill traffic on a kernel that is bound by shared-memory bandwidth
+    static const int conv_bres_env = [] { const char* e = getenv("SPG_CONV_BRES"); return e ? atoi(e) : 1; }();
+    a.b_resident = (conv_bres_env && a.halo && !a.pair && 9 * a.cin_chunks * a.block_n * 128 <= 80 * 1024 &&
+                    a.num_m_tiles * a.num_n_tiles >= 4 * sm_count()) ? 1 : 0;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, tile_h, a.halo ? 130 : tile_w)) return rc;
     if (int rc = make_tmap_2d(&tb, w, Cout, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;

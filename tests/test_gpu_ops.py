@@ -92,7 +92,7 @@ def test_linear_rejects_bad_shapes(ops):
 
 
 @pytest.mark.parametrize("B,H,Cin,Cout,head", [(2, 16, 64, 64, False), (1, 64, 256, 64, True), (1, 128, 320, 256, True),
-                                               (1, 256, 128, 128, False)])
+                                               (1, 256, 128, 128, False), (2, 512, 64, 64, True)])  # last: resident weights
 def test_conv3x3(ops, B, H, Cin, Cout, head):
     g = torch.Generator(device="cuda").manual_seed(H + Cin)
     x = _bf(torch.randn(B, H, H, Cin, device="cuda", generator=g))
@@ -409,7 +409,7 @@ def test_fp16_stores_saturate(ops):
     assert bool(torch.isfinite(z.float()).all())
 
 
-@pytest.mark.parametrize("M,N,K,res_rows", [(16384, 576, 2304, 0), (16384, 576, 576, 0), (1000, 576, 576, 0),
+@pytest.mark.parametrize("M,N,K,res_rows", [(16384, 576, 2304, 0), (12928, 576, 2304, 0), (16384, 576, 576, 0), (1000, 576, 576, 0),
                                             (4096, 288, 1152, 0), (20000, 288, 288, 0), (2000, 144, 576, 0),
                                             (4096, 144, 168, 1024), (128, 576, 2304, 0)])
 def test_layernorm_applied_by_the_producer(ops, M, N, K, res_rows):
