@@ -894,6 +894,12 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     const bool pair = a.pair != 0;
     a.reverse = ctx.reverse ? 1 : 0;
     const int bn_cta = pair ? a.block_n / 2 : a.block_n;  // weight rows staged per CTA
+    const int staging_all = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
+                            (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0) +
+                            (a.ln_mode == 3 ? a.epi_warps * kLnSlots * kLnBufBytes + kLnXBytes : 0);
+    if (a.b_resident && !a.halo &&
+        kSmemBudget - (1024 + kBarBytes + kEpiScratch + 1024 + staging_all) - a.num_k_chunks * bn_cta * 128 < 4 * kAStageBytes)
+        a.b_resident = 0;  // the resident weight tile would leave fewer than four A stages
     a.b_res_tiles = a.b_resident ? (a.halo ? 9 * a.cin_chunks : a.num_k_chunks) : 0;
     const int b_res_bytes = a.b_res_tiles * bn_cta * 128;
     const int stage_bytes = a.b_resident ? (a.halo ? kHaloABytes : kAStageBytes)
@@ -1150,7 +1156,10 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     decide_pair(a);
     // resident weights: short K, plain tiling (N a multiple of block_n), enough tiles that the ring depth matters
     static const int bres_env = [] { const char* e = getenv("SPG_GEMM_BRES"); return e ? atoi(e) : 1; }();
-    a.b_resident = (bres_env && !a.pair && a.num_k_chunks <= 3 && N % a.block_n == 0 && a.num_n_tiles <= 16 &&
+    // (K <= 192: 2-3 tiles in flight instead of 1.3; K <= 320 with a 144-wide tile: same ring depth in tiles, but no
+    // weight refill traffic on kernels whose MMAs are paced by shared-memory bandwidth -- launch_gemm drops the mode again
+    // if fewer than four A stages would fit next to the resident tile)
+    a.b_resident = (bres_env && !a.pair && a.num_k_chunks <= (bres_env >= 2 ? 3 : 5) && N % a.block_n == 0 && a.num_n_tiles <= 16 &&
                     a.num_m_tiles * a.num_n_tiles >= 4 * sm_count() && a.ln_mode != 1 && a.ln_mode != 2) ? 1 : 0;
     static const int l2pf_env = [] { const char* e = getenv("SPG_GEMM_L2PF"); return e ? atoi(e) : 1; }();
     // pays on short reductions without a residual stream (fc1 +3.5 %, QKV +2 %); with K = 2304 and an fp32 residual

@@ -526,7 +526,7 @@ def test_no_writes_outside_the_outputs(ops):
 
 
 @pytest.mark.parametrize("M,N,K,act", [(40000, 432, 144, 0), (30001, 576, 144, 2), (80000, 144, 168, 0), (33000, 864, 144, 0),
-                                       (26000, 288, 144, 0)])
+                                       (26000, 288, 144, 0), (20000, 864, 288, 0), (45000, 288, 288, 0)])
 def test_linear_resident_weights(ops, M, N, K, act):
     """Short-K GEMMs with many tiles run in the resident-weight mode (the CTA's weight tile is loaded once, the ring
     holds A chunks only, grid = a multiple of the n-tiles): ragged M, K tails (144 = 2*64 + 16), GELU, fp32 output."""
