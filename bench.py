@@ -597,7 +597,9 @@ def main():
                      "traffic_detail": NCU_TRAFFIC, "peak_source": f"{peak_src} sustained bf16",
                      "launches_per_step": m["n_gemm"] // max(args.steps, 1),
                      "kernel_ms_per_step": round(m["gemm_ms"] / args.steps, 3),
-                     "share_of_step": round(m["gemm_ms"] / (m["rank_ms_per_step"] * args.steps), 4)},
+                     "share_of_step": round(m["gemm_ms"] / (m["rank_ms_per_step"] * args.steps), 4),
+                     "note": "time of all 210 GEMM / conv launches incl. the LayerNorm passes that 44 of them now apply in "
+                             "their epilogues (round 1 ran those as 44 separate kernels outside this number)"},
         "model_roofline": {"gflop_per_image": gflop_img, "achieved_tflops_per_gpu": round(model_tf, 1),
                            "frac_of_sustained_peak": round(model_tf / peak_tf, 4),
                            "note": "algorithmic FLOPs of the reference formulation (SURVEY.md 8(d)) / whole step time"},
