@@ -135,7 +135,10 @@ int spg_linear_h16(const void* A, const void* W, int M, int N, int K, const spg_
 /*
  * 3x3, stride 1, zero-pad 1 convolution as an implicit GEMM: x is NHWC bf16 [B,H,W,Cin]
  * (Cin % 64 == 0), w is [Cout, 9*Cin] bf16 with k = (ky*3+kx)*Cin + ci; the halo is produced by
- * TMA out-of-bounds zero fill, nothing is materialised.  out is [B*H*W, Cout].
+ * TMA out-of-bounds zero fill, nothing is materialised.  out is [B*H*W, Cout].  A tile is 128 pixels (tile_h x tile_w) of
+ * one image: W may divide 128, be a multiple of 128, or be anything else >= 32 (e.g. 44 / 88 / 176 at a 352 x 352 input),
+ * in which case 64- / 128-pixel tile columns are used and the last one is ragged (its missing pixels are zero fill on the
+ * way in and clipped by an NHWC store map on the way out; 16-bit outputs only); H must be a multiple of tile_h.
  * Replaces nn.Conv2d(k=3,p=1) + BatchNorm2d(eval) + ReLU in EdgeDetectionModule and DecoderBlock
  * (models/object_detection.py:115-123,150-152,193-198,230-236).
  */
@@ -156,7 +159,8 @@ int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W, int Cin, 
  *   corr [2][B*H][4*Cout] fp32: pre-activation corrections of the first (side 0) / last (side 1) image COLUMN, the
  *       same border effect along x: corr = spg_up2_border_gather_h16(x) @ delta_w^T via spg_linear_h16.
  *   bias4 [4*Cout] fp32 (the folded BatchNorm shift repeated per phase).
- * W % 128 == 0, Cin % 64 == 0, Cout % 32 == 0, Cout <= 64.  The host-side weight folding is spegnet_b200/model.py
+ * W >= 32 (a tile is 128 pixels of one low-resolution row; the last tile of a row may be ragged), Cin % 64 == 0,
+ * Cout % 32 == 0, Cout <= 64.  The host-side weight folding is spegnet_b200/model.py
  * (`up2_phase_weights`), pinned against F.interpolate + F.conv2d in tests/test_host.py and tests/test_gpu_ops.py.
  */
 int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const float* corr, int B, int H, int W, int Cin, int Cout,
@@ -172,6 +176,16 @@ int spg_up2_border_gather_h16(const void* x, void* out, int B, int H, int W, int
  */
 int spg_layernorm_f32_h16(const float* x, const float* gamma, const float* beta, void* y, int M, int C,
                            float eps, const spg_launch_t* launch);
+
+/*
+ * dst[b, y, x, :] = src[b, y, x, :] for y < H, x < W between two NHWC token grids [B, Hs, Ws, C] -> [B, Hd, Wd, C]
+ * (h16, C % 8 == 0); the rest of dst is left untouched.  Window attention on a grid that does not tile into windows
+ * (input sizes that are not multiples of 256): the norm1 output is copied into a zero-initialised padded grid before
+ * the qkv projection -- the padded tokens are zeros there and take part in the softmax as keys, exactly as
+ * window_partition does (HF:modeling_sam2.py:395-399) -- and the attention output is cropped back (:435-437).
+ */
+int spg_copy_grid_h16(const void* src, int Hs, int Ws, void* dst, int Hd, int Wd, int B, int H, int W, int C,
+                      const spg_launch_t* launch);
 
 /*
  * The same LayerNorm, BIT-IDENTICAL to what a residual GEMM with spg_epilogue_t.ln_apply_* stores for the same rows

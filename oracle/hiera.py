@@ -107,18 +107,24 @@ def _pool2x2_nhwc(t: torch.Tensor, stride: int) -> torch.Tensor:
     return F.max_pool2d(t.permute(0, 3, 1, 2), kernel_size=stride, stride=stride).permute(0, 2, 3, 1)
 
 
-def _to_windows(t: torch.Tensor, ws: int) -> torch.Tensor:
+def _to_windows(t: torch.Tensor, ws: int):
+    """[B,h,w,C] -> ([B*nW, ws, ws, C], (hp, wp)).  A grid that does not tile into ws x ws windows is padded with ZERO
+    tokens at the bottom / right first (HF:modeling_sam2.py:395-399): the padding happens after norm1, so the padded
+    tokens reach the qkv projection as zeros, come out as its bias, and take part in the window's softmax as keys."""
     b, h, w, c = t.shape
-    if h % ws or w % ws:
-        raise ValueError(f"{h}x{w} tokens do not tile into {ws}x{ws} windows (resolution outside the supported set)")
-    t = t.reshape(b, h // ws, ws, w // ws, ws, c).permute(0, 1, 3, 2, 4, 5)
-    return t.reshape(b * (h // ws) * (w // ws), ws, ws, c)
+    ph, pw = (ws - h % ws) % ws, (ws - w % ws) % ws
+    if ph or pw:
+        t = F.pad(t, (0, 0, 0, pw, 0, ph))
+    hp, wp = h + ph, w + pw
+    t = t.reshape(b, hp // ws, ws, wp // ws, ws, c).permute(0, 1, 3, 2, 4, 5)
+    return t.reshape(b * (hp // ws) * (wp // ws), ws, ws, c), (hp, wp)
 
 
-def _from_windows(t: torch.Tensor, ws: int, b: int, h: int, w: int) -> torch.Tensor:
+def _from_windows(t: torch.Tensor, ws: int, b: int, hp: int, wp: int, h: int, w: int) -> torch.Tensor:
+    """Inverse of `_to_windows` on the padded grid, then crop to the h x w valid tokens (HF:...:417-438)."""
     c = t.shape[-1]
-    t = t.reshape(b, h // ws, w // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5)
-    return t.reshape(b, h, w, c)
+    t = t.reshape(b, hp // ws, wp // ws, ws, ws, c).permute(0, 1, 3, 2, 4, 5)
+    return t.reshape(b, hp, wp, c)[:, :h, :w]
 
 
 def pos_embed_map(pos_embed: torch.Tensor, pos_embed_window: torch.Tensor, h: int, w: int) -> torch.Tensor:
@@ -141,7 +147,7 @@ def block_forward(sd: Dict[str, torch.Tensor], pre: str, x: torch.Tensor, spec: 
     ws = spec.window if spec.window > 0 else h
     if spec.window == 0 and h != w:
         raise ValueError("global attention restated for square token grids only")
-    tokens = _to_windows(y, ws)  # [nW, ws, ws, C]
+    tokens, (hp, wp) = _to_windows(y, ws)  # [nW, ws, ws, C]
     nw = tokens.shape[0]
     qkv = F.linear(tokens.reshape(nw, ws * ws, spec.dim_in), sd[pre + "attn.qkv.weight"], sd[pre + "attn.qkv.bias"])
     qkv = qkv.reshape(nw, ws * ws, 3, spec.heads, hd)
@@ -162,7 +168,8 @@ def block_forward(sd: Dict[str, torch.Tensor], pre: str, x: torch.Tensor, spec: 
         ctx = torch.einsum("whqk,wkhd->wqhd", probs, v).reshape(nw, ws_out, ws_out, spec.dim_out)
     ctx = F.linear(ctx, sd[pre + "attn.proj.weight"], sd[pre + "attn.proj.bias"])
     ho, wo = (h // spec.q_stride, w // spec.q_stride) if spec.q_stride else (h, w)
-    x = skip + _from_windows(ctx, ws_out, b, ho, wo)
+    hpo, wpo = (hp // spec.q_stride, wp // spec.q_stride) if spec.q_stride else (hp, wp)  # HF:...:514-521
+    x = skip + _from_windows(ctx, ws_out, b, hpo, wpo, ho, wo)
 
     z = F.layer_norm(x, (spec.dim_out,), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"], eps)
     z = F.linear(z, sd[pre + "mlp.layers.0.weight"], sd[pre + "mlp.layers.0.bias"])

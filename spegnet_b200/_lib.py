@@ -53,6 +53,7 @@ SIGNATURES = {
     "spg_up2_border_gather_h16": [_P, _P, _I, _I, _I, _I, _P],
     "spg_layernorm_f32_h16": [_P, _P, _P, _P, _I, _I, _F, _P],
     "spg_layernorm_matched_f32_h16": [_P, _P, _P, _P, _I, _I, _F, _P],
+    "spg_copy_grid_h16": [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P],
     "spg_patchify_7x7s4": [_P, _P, _I, _I, _P],
     "spg_maxpool2x2_f32": [_P, _P, _I, _I, _I, _I, _P],
     "spg_cast_f32_h16": [_P, _P, _LL, _P],

@@ -151,6 +151,19 @@ int make_tmap_epilogue(CUtensorMap* out, const void* base, uint64_t rows, uint64
                                    : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
 }
 
+int make_tmap_epilogue_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                            uint32_t box_cols) {
+    const uint64_t row_bytes = box_cols * 2;
+    if (row_bytes != 32 && row_bytes != 64 && row_bytes != 128) return fail(SPG_ERR_INVALID, "bad epilogue box");
+    if ((C * 2) % 16 != 0) return fail(SPG_ERR_INVALID, "channel pitch must be a multiple of 16 bytes");
+    cuuint64_t dims[4] = {C, W, H, B};
+    cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+    cuuint32_t box[4] = {box_cols, 32, 1, 1};
+    return encode(out, base, 4, dims, strides, box, -1,
+                  row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B));
+}
+
 int make_tmap_up2_out(CUtensorMap* out, const void* base, uint64_t BH, uint64_t W, uint64_t C, uint32_t box_cols) {
     const uint64_t row_bytes = box_cols * 2;
     if (row_bytes != 32 && row_bytes != 64 && row_bytes != 128) return fail(SPG_ERR_INVALID, "bad epilogue box");

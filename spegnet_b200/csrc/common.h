@@ -46,6 +46,12 @@ int make_tmap_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, u
 int make_tmap_epilogue(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, int elem_is_f32,
                        uint32_t box_cols);
 
+// The same 32-pixel x box_cols epilogue tile, but addressed as pixels of an NHWC map [B, H, W, C] (16-bit): box =
+// {box_cols, 32 pixels of one image row, 1, 1}; pixels with x >= W are clipped by the TMA unit.  Used by convolutions
+// whose width is not a multiple of their tile width.
+int make_tmap_epilogue_nhwc(CUtensorMap* out, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                            uint32_t box_cols);
+
 // Pixel-shuffle store map of the fused "bilinear x2 -> 3x3 conv" kernel: out [B, 2H, 2W, C] viewed as the 5-D tensor
 // [C, 2 (column phase), W, 2 (row phase), B*H]; a box {box_cols, 1, 32, 1, 1} is 32 low-resolution pixels of one
 // output phase -- in shared memory the same 32 x box_cols tile the 2-D epilogue map stores.

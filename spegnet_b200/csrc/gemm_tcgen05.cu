@@ -84,6 +84,11 @@ struct GemmArgs {
     // conv mode
     int conv;
     int H, W, cin_chunks, tile_w;
+    // conv modes: an m-tile is tile_h x tile_w pixels (tile_h * tile_w = 128) of one image; tiles_x tiles cover an image
+    // row band (tiles_x * tile_w >= W), tiles_img = tiles_x * H / tile_h tiles an image.  `ragged` (W % tile_w != 0): the
+    // pixels with x >= W of the last tile column do not exist -- their A rows are TMA zero fill, their outputs are
+    // clipped by a 4-D store map / skipped by the fused head.
+    int tiles_x, tiles_img, ragged;
     // fused bilinear x2 upsample (kUp2 instances): the conv runs on the LOW-resolution grid with 4 output phases stacked
     // along N; w holds one [N, K] weight set per row class (top / interior / bottom image row), corr the pre-activation
     // corrections of the first / last image column, the store is a pixel shuffle (see spg_conv3x3_up2_h16)
@@ -245,7 +250,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const int hw = p.H * p.W;
             // pair mode: both CTAs load; all transaction bytes are signalled on the leader's full barrier
             const uint32_t n_half = kPair ? rank * (p.block_n / 2) : 0u;  // this CTA's slice of the weight tile
             [[maybe_unused]] int trace_i = 0;
@@ -266,11 +270,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int m_blk = kPair ? 2 * m_unit + static_cast<int>(rank) : m_unit;  // this CTA's 128-row block
                 int img = 0, y0 = 0, x0 = 0;
                 if (p.conv) {
-                    const int m0 = m_blk * kBlockM;
-                    img = m0 / hw;
-                    const int rem = m0 - img * hw;
-                    y0 = rem / p.W;
-                    x0 = rem - y0 * p.W;
+                    img = m_blk / p.tiles_img;
+                    const int rem = m_blk - img * p.tiles_img;
+                    const int ty = rem / p.tiles_x;
+                    y0 = ty * (kBlockM / p.tile_w);
+                    x0 = (rem - ty * p.tiles_x) * p.tile_w;
                 }
                 // The first touch of an m-block's A rows comes from HBM (the weights and every later n-tile hit L2), and the
                 // ring only looks `stages` k-chunks (~1.5 us) ahead: each tile would start with an HBM-latency bubble
@@ -503,13 +507,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             // kUp2: position of this warp's 32 low-resolution pixels, and the correction row of a border-column pixel
             int up_img_row = 0, up_x = 0;
             const float* corr_row = nullptr;
+            // conv modes: image / row / column of this warp's 32 pixels (they lie in one image row: tile_w >= 32)
+            int cv_img = 0, cv_y = 0, cv_x = 0;
+            if (p.conv) {
+                cv_img = m_blk / p.tiles_img;
+                const int rem = m_blk - cv_img * p.tiles_img;
+                const int ty = rem / p.tiles_x;
+                const int pix0 = quarter * 32;
+                cv_y = ty * (kBlockM / p.tile_w) + pix0 / p.tile_w;
+                cv_x = (rem - ty * p.tiles_x) * p.tile_w + pix0 % p.tile_w;
+            }
             if (kUp2) {
-                const int hw = p.H * p.W;
-                const int img = row0 / hw;
-                const int rem = row0 - img * hw;
-                const int y = rem / p.W;
-                up_x = rem - y * p.W;
-                up_img_row = img * p.H + y;
+                up_x = cv_x;
+                up_img_row = cv_img * p.H + cv_y;
                 const int x = up_x + lane;
                 if (x == 0) corr_row = p.corr + static_cast<size_t>(up_img_row) * p.N + n0;
                 else if (x == p.W - 1) corr_row = p.corr + (static_cast<size_t>(p.bh) + up_img_row) * p.N + n0;
@@ -696,6 +706,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 const int phase = n / p.cout;  // (row phase, column phase) = (phase >> 1, phase & 1)
                                 tma_store_5d(&tmap_out, my_staging + slot * p.buf_bytes, n - phase * p.cout, phase & 1, up_x,
                                              phase >> 1, up_img_row);
+                            } else if (p.ragged) {  // [C, W, H, B] map: columns x >= W of the last tile column are clipped
+                                tma_store_4d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, cv_x, cv_y, cv_img);
                             } else {
                                 tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, row0);
                             }
@@ -819,7 +831,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (part == 0 && row_ok) {
 #pragma unroll
                     for (int k = 1; k < kParts; ++k) head_acc += headp_s[(k - 1) * 128 + row_in_tile];
-                    p.head_out[row] = head_acc + p.head_b;
+                    if (!p.ragged) p.head_out[row] = head_acc + p.head_b;
+                    else if (cv_x + lane < p.W)  // head_out is the compact [B, H, W] map
+                        p.head_out[(static_cast<size_t>(cv_img) * p.H + cv_y) * p.W + cv_x + lane] = head_acc + p.head_b;
                 }
             }
             acc ^= 1;
@@ -1178,16 +1192,22 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     SPG_CHECK_ARG(B > 0 && H > 0 && W > 0, "bad conv shape B=%d H=%d W=%d", B, H, W);
     SPG_CHECK_ARG(Cin % kBlockK == 0, "Cin=%d must be a multiple of 64", Cin);
     SPG_CHECK_ARG(Cout % 16 == 0, "Cout=%d must be a multiple of 16", Cout);
-    const int tile_w = W < kBlockM ? W : kBlockM;
-    SPG_CHECK_ARG(kBlockM % tile_w == 0 && W % tile_w == 0, "W=%d must divide or be a multiple of 128", W);
+    // tile = tile_h x tile_w pixels of one image.  Widths that divide 128 or are multiples of 128 tile exactly; any other
+    // width (e.g. 44 / 88 / 176 / 352 at a 352 x 352 input) takes 64- or 128-pixel tile columns whose last one is ragged
+    int tile_w = W < kBlockM ? W : kBlockM;
+    if (kBlockM % tile_w != 0 || W % tile_w != 0) tile_w = W <= 64 ? 64 : kBlockM;
     const int tile_h = kBlockM / tile_w;
     SPG_CHECK_ARG(H % tile_h == 0, "H=%d must be a multiple of the tile height %d", H, tile_h);
     GemmArgs a{};
     EpiMaps em;
-    a.M = B * H * W;
+    a.tiles_x = (W + tile_w - 1) / tile_w;
+    a.tiles_img = a.tiles_x * (H / tile_h);
+    a.ragged = W % tile_w != 0 ? 1 : 0;
+    SPG_CHECK_ARG(!a.ragged || tile_w >= 32, "ragged conv tiles need >= 32 pixels per row");
+    a.num_m_tiles = B * a.tiles_img;
+    a.M = a.num_m_tiles * kBlockM;  // tile pixels (== B*H*W unless ragged)
     a.N = Cout;
     a.block_n = pick_block_n(Cout);
-    a.num_m_tiles = a.M / kBlockM;
     a.num_n_tiles = Cout / a.block_n;
     a.cin_chunks = Cin / kBlockK;
     a.num_k_chunks = 9 * a.cin_chunks;
@@ -1201,7 +1221,11 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     // the three dx taps through shifted descriptors: 1.5-1.9x fewer bytes per FLOP than one A tile per tap.
     a.halo = (tile_h == 1 && a.block_n <= 128) ? 1 : 0;
     if (a.halo) a.num_k_chunks = 3 * a.cin_chunks;
-    if (int rc = fill_epilogue(a, em, ep, a.M, Cout)) return rc;
+    if (int rc = fill_epilogue(a, em, ep, B * H * W, Cout)) return rc;
+    if (a.ragged && a.has_out) {  // pixels of the last tile column beyond W must be clipped: address the output as NHWC
+        SPG_CHECK_ARG(!a.out_f32, "ragged conv widths support 16-bit outputs only");
+        if (int rc = make_tmap_epilogue_nhwc(&em.out, ep->out, B, H, W, Cout, a.group * 16)) return rc;
+    }
     decide_pair(a);
     // narrow row-halo convs whose nine tap tiles fit next to a deep A ring keep the weights resident (Cout = 64,
     // Cin = 64: 72 KB): no weight refill traffic on a kernel that is bound by shared-memory bandwidth
@@ -1221,15 +1245,18 @@ extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const flo
     SPG_CHECK_ARG(B > 0 && H >= 2 && W > 0, "bad shape B=%d H=%d W=%d", B, H, W);
     SPG_CHECK_ARG(Cin % kBlockK == 0, "Cin=%d must be a multiple of 64", Cin);
     SPG_CHECK_ARG(Cout % 32 == 0 && 4 * Cout <= 256, "Cout=%d must be a multiple of 32 and <= 64 (4 phases in one 256-wide tile)", Cout);
-    SPG_CHECK_ARG(W % kBlockM == 0, "W=%d must be a multiple of 128 (a tile is 128 pixels of one low-resolution row)", W);
+    SPG_CHECK_ARG(W >= 32, "W=%d: a tile is 128 pixels of one low-resolution row (the last tile of a row may be ragged)", W);
     SPG_CHECK_ARG((reinterpret_cast<uintptr_t>(corr) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias4) & 15) == 0,
                   "corr / bias4 must be 16-byte aligned");
     GemmArgs a{};
     EpiMaps em;
-    a.M = B * H * W;
+    a.tiles_x = (W + kBlockM - 1) / kBlockM;
+    a.tiles_img = a.tiles_x * H;
+    a.ragged = W % kBlockM != 0 ? 1 : 0;  // the pixel-shuffle store map clips x >= W by itself
+    a.num_m_tiles = B * a.tiles_img;
+    a.M = a.num_m_tiles * kBlockM;
     a.N = 4 * Cout;
     a.block_n = a.N;
-    a.num_m_tiles = a.M / kBlockM;
     a.num_n_tiles = 1;
     a.cin_chunks = Cin / kBlockK;
     a.num_k_chunks = 9 * a.cin_chunks;
@@ -1255,7 +1282,7 @@ extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const flo
     memset(&em, 0, sizeof(em));
     if (int rc = make_tmap_up2_out(&em.out, out, static_cast<uint64_t>(B) * H, W, Cout, 32)) return rc;
     decide_pair(a);
-    if (W % (2 * kBlockM) != 0) a.pair = 0;  // both CTAs of a pair must sit in the same image row (same weight set)
+    if (a.tiles_x % 2 != 0) a.pair = 0;  // both CTAs of a pair must sit in the same image row (same weight set)
     CUtensorMap ta, tb;
     if (int rc = make_tmap_nhwc(&ta, x, B, H, W, Cin, 1, kBlockM)) return rc;
     if (int rc = make_tmap_2d(&tb, w_phase, 3ull * a.N, 9ull * Cin, 18ull * Cin, a.pair ? a.block_n / 2 : a.block_n)) return rc;

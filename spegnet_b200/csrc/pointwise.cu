@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kAsppThreads) aspp_kernel(const AsppParams p, 
             float acc[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-            if (y0 < H) {
+            if (y0 < H && pix < band_rows * W) {
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int yy = y0 + (tap / 3 - 1) * d, xx = x0 + (tap % 3 - 1) * d;
@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(kAsppThreads) aspp_kernel(const AsppParams p, 
     for (int q = 0; q < kAsppPix; ++q) {
         const int pix = threadIdx.x + q * kAsppThreads;
         const int y0 = y_band + pix / W, x0 = pix % W;
-        if (y0 >= H) continue;
+        if (y0 >= H || pix >= band_rows * W) continue;  // (the band holds band_rows * W <= 2048 pixels)
         float o[8];
 #pragma unroll
         for (int g = 0; g < 8; ++g) o[g] = fmaxf(out_acc[q][g] + __ldg(p.wf_bias + 8 * t + g), 0.f);
@@ -633,6 +633,23 @@ __global__ void __launch_bounds__(128) layernorm_sliced_kernel(const float* __re
     }
 }
 
+// dst[b, y, x, :] = src[b, y, x, :] for y < H, x < W between two NHWC layouts [B, Hs, Ws, C] -> [B, Hd, Wd, C] (16-byte
+// vectors): the zero-padded token grid that window attention needs when the grid does not tile into windows
+// (HF:modeling_sam2.py:395-399 pads after norm1), and the crop after it (:435-437).  The rest of dst is not touched.
+__global__ void __launch_bounds__(256) copy_grid_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int H, int W,
+                                                        int Hs, int Ws, int Hd, int Wd, int cv, long long total) {
+    pdl_prologue();
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+        const int v = static_cast<int>(i % cv);
+        long long t = i / cv;
+        const int x = static_cast<int>(t % W);
+        t /= W;
+        const int y = static_cast<int>(t % H);
+        const long long b = t / H;
+        dst[((b * Hd + y) * Wd + x) * cv + v] = __ldg(src + ((b * Hs + y) * Ws + x) * cv + v);
+    }
+}
+
 inline unsigned blocks_for(long long total, int per_block = 256) {
     return static_cast<unsigned>((total + per_block - 1) / per_block);
 }
@@ -676,6 +693,18 @@ extern "C" int spg_layernorm_f32_h16(const float* x, const float* gamma, const f
         else
             SPG_CHECK_CUDA((launch_pdl(layernorm_kernel<32, 9>, grid, 256, 0, st, x, gamma, beta, yo, M, C, eps, rpw, st.reverse ? 1 : 0)));
     }
+    SPG_LAUNCHED();
+    return SPG_OK;
+}
+
+extern "C" int spg_copy_grid_h16(const void* src, int Hs, int Ws, void* dst, int Hd, int Wd, int B, int H, int W, int C,
+                                 const spg_launch_t* launch) {
+    SPG_CHECK_ARG(src && dst, "null pointer");
+    SPG_CHECK_ARG(B > 0 && H > 0 && W > 0 && H <= Hs && W <= Ws && H <= Hd && W <= Wd, "bad grid copy %dx%d from %dx%d to %dx%d", H, W, Hs, Ws, Hd, Wd);
+    SPG_CHECK_ARG(C % 8 == 0, "C=%d must be a multiple of 8 (16-byte vectors)", C);
+    const long long total = static_cast<long long>(B) * H * W * (C / 8);
+    SPG_CHECK_CUDA((launch_pdl(copy_grid_kernel, capped_blocks(total), 256, 0, LaunchCtx(launch), static_cast<const uint4*>(src),
+                               static_cast<uint4*>(dst), H, W, Hs, Ws, Hd, Wd, C / 8, total)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -779,7 +808,7 @@ extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* d
     AsppParams p{static_cast<const uint4*>(x), dw, dw_bias, gvec, wf, wf_bias, static_cast<uint4*>(y), B, H, W,
                  {dilations[0], dilations[1], dilations[2], dilations[3]}};
     // band = 2048 pixels (4 per thread); shared memory holds the band plus the largest dilation above and below
-    SPG_CHECK_ARG(W <= 2048 && (kAsppThreads * kAsppPix) % W == 0, "e-ASPP needs W to divide 2048 (W=%d)", W);
+    SPG_CHECK_ARG(W <= 2048, "e-ASPP needs W <= 2048 (W=%d)", W);
     const int band_rows = kAsppThreads * kAsppPix / W;
     int dmax = 0;
     for (int i = 0; i < 4; ++i) dmax = dilations[i] > dmax ? dilations[i] : dmax;

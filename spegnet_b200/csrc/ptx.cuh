@@ -140,6 +140,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src,
                  : "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int32_t c0, int32_t c1, int32_t c2,
                                              int32_t c3, int32_t c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"

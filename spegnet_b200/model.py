@@ -135,7 +135,8 @@ class LazyFeatures(Mapping):
 class _Workspace:
     """Device buffers for one (batch, resolution); reused across forwards on the same stream."""
 
-    def __init__(self, B: int, S: int, dev: torch.device, spec: TrunkSpec, h16: torch.dtype, ln_records: bool = False):
+    def __init__(self, B: int, S: int, dev: torch.device, spec: TrunkSpec, h16: torch.dtype, ln_records: bool = False,
+                 blocks=()):
         bf, f32 = h16, torch.float32
         d = spec.dims
         G = S // 4
@@ -170,6 +171,24 @@ class _Workspace:
         self.d3a = e(B * 64 * h * h * 64, bf).view(B, 8 * h, 8 * h, 64)
         # LayerNorm row records {c, P, (sum, sum sq) x P} of the residual stream, ping-pong (see spg_epilogue_t)
         self.rec = [e(T[0] * 32, f32).view(T[0], 32) for _ in range(2)] if ln_records else None
+        # window attention on grids that do not tile into the block's windows (S not a multiple of 256): zero-initialised
+        # padded norm1 outputs per (padded edge, channels) -- only their valid region is ever rewritten -- and the padded
+        # qkv / attention-output scratch
+        self.ypad: Dict[Tuple[int, int], torch.Tensor] = {}
+        qp = ap = 0
+        Hs = G
+        for b in blocks:
+            if b.window and Hs % b.window:
+                Hp = -(-Hs // b.window) * b.window
+                if (Hp, b.dim_in) not in self.ypad:
+                    self.ypad[(Hp, b.dim_in)] = torch.zeros(B, Hp, Hp, b.dim_in, dtype=bf, device=dev)
+                Hop = Hp // 2 if b.q_pool else Hp
+                qp = max(qp, B * Hp * Hp * 3 * b.dim_out)
+                ap = max(ap, B * Hop * Hop * b.dim_out)
+            if b.q_pool:
+                Hs //= 2
+        self.qkvp = e(qp, bf) if qp else None
+        self.attp = e(ap, bf) if ap else None
         self.pos: Optional[torch.Tensor] = None  # [G*G, 144] fp32, set by the model (input independent)
 
 
@@ -404,9 +423,9 @@ class SPEGNet(nn.Module):
         B, Cin, S, S2 = x.shape
         if Cin != 3 or S != S2:
             raise ValueError(f"Expected square RGB input [B,3,S,S], got {tuple(x.shape)}")
-        if (S // 4) % 8 or (S // 16) % 16:
-            # other S % 32 == 0 sizes would need padded windows (HF:modeling_sam2.py:395-399)
-            raise ValueError(f"resolution {S} is outside the supported set (multiples of 256, e.g. 512 / 1024)")
+        # any S % 32 == 0 (352, 384, ... as well as 512 / 1024): token grids that do not tile into the block's windows
+        # run through zero-padded grids around the attention (HF:modeling_sam2.py:395-399, `_trunk`), and the head's
+        # convolutions take a ragged last tile column (spg_conv3x3_h16)
         if not x.is_cuda:
             raise RuntimeError("spegnet_b200.SPEGNet needs a CUDA tensor on a B200; there is no CPU fallback")
         if self._packed is None:
@@ -420,7 +439,7 @@ class SPEGNet(nn.Module):
             return self._forward_eager(x, B, S)
 
     def _new_workspace(self, x: torch.Tensor, B: int, S: int) -> _Workspace:
-        ws = _Workspace(B, S, x.device, self.spec, self.compute_dtype, ln_records=self.ln_fuse)
+        ws = _Workspace(B, S, x.device, self.spec, self.compute_dtype, ln_records=self.ln_fuse, blocks=self.blocks)
         ws.pos = self._pos_map(self._packed, S // 4).to(x.device)
         return ws
 
@@ -466,7 +485,7 @@ class SPEGNet(nn.Module):
                 "features": LazyFeatures({k: v.clone() for k, v in raw.items()})}
 
     def _trunk(self, W, ws: _Workspace, x: torch.Tensor, B: int, S: int) -> None:
-        if self.ln_fuse and self._debug_taps is None and ws.rec is not None:
+        if self.ln_fuse and self._debug_taps is None and ws.rec is not None and not ws.ypad:
             return self._trunk_ln_folded(W, ws, x, B, S)
         G = S // 4
         blocks = self.blocks
@@ -511,10 +530,24 @@ class SPEGNet(nn.Module):
                 ops.maxpool2x2(proj, nxt, B, H, H, b.dim_out)  # pooled shortcut lands in the new stream
             else:
                 Ho, Mo, nxt = H, M, cur
-            qkv = ws.qkv[: M * 3 * b.dim_out].view(M, 3 * b.dim_out)
-            ops.linear(y, W[p + "qkv.w"], qkv, bias=W[p + "qkv.b"])
             att = ws.att[: Mo * b.dim_out].view(Mo, b.dim_out)
-            ops.window_attention(qkv, att, B, H, H, b.dim_out, b.heads, b.window, b.q_pool)
+            if b.window and H % b.window:
+                # the grid does not tile into this block's windows: norm1 output -> zero-padded grid -> qkv (the padded
+                # tokens come out as the bias and act as keys) -> window attention on the padded grid -> crop
+                # (window_partition / window_unpartition, HF:modeling_sam2.py:395-399, 435-437, 514-521)
+                Hp = -(-H // b.window) * b.window
+                Hop = Hp // 2 if b.q_pool else Hp
+                yp = ws.ypad[(Hp, b.dim_in)]
+                ops.copy_grid(y.view(B, H, H, b.dim_in), yp, H, H)
+                qkv = ws.qkvp[: B * Hp * Hp * 3 * b.dim_out].view(B * Hp * Hp, 3 * b.dim_out)
+                ops.linear(yp.view(B * Hp * Hp, b.dim_in), W[p + "qkv.w"], qkv, bias=W[p + "qkv.b"])
+                attp = ws.attp[: B * Hop * Hop * b.dim_out].view(B, Hop, Hop, b.dim_out)
+                ops.window_attention(qkv, attp.view(-1, b.dim_out), B, Hp, Hp, b.dim_out, b.heads, b.window, b.q_pool)
+                ops.copy_grid(attp, att.view(B, Ho, Ho, b.dim_out), Ho, Ho)
+            else:
+                qkv = ws.qkv[: M * 3 * b.dim_out].view(M, 3 * b.dim_out)
+                ops.linear(y, W[p + "qkv.w"], qkv, bias=W[p + "qkv.b"])
+                ops.window_attention(qkv, att, B, H, H, b.dim_out, b.heads, b.window, b.q_pool)
             # attention projection + residual; its output feeds norm2
             ap, z, ln2 = ln_after(b.dim_out, p + "n2", Mo, False)
             ops.linear(att, W[p + "ap.w"], nxt, bias=W[p + "ap.b"], residual=nxt, ln_apply=ap)

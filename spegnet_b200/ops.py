@@ -192,6 +192,17 @@ def layernorm_matched(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, 
     _lib.check(rc, "spg_layernorm_matched_f32_h16", dn)
 
 
+def copy_grid(src: torch.Tensor, dst: torch.Tensor, H: int, W: int) -> None:
+    """dst[:, :H, :W] = src[:, :H, :W] for h16 NHWC grids [B,Hs,Ws,C] / [B,Hd,Wd,C] (pad / crop of a token grid)."""
+    B, Hs, Ws, Cc = src.shape
+    Bd, Hd, Wd, Cd = dst.shape
+    if B != Bd or Cc != Cd:
+        raise ValueError(f"grids differ in batch / channels: {tuple(src.shape)} vs {tuple(dst.shape)}")
+    lib, dn = _lib_for(src)
+    rc = lib.spg_copy_grid_h16(_ptr(src, H16, "src"), Hs, Ws, _ptr(dst, H16, "dst"), Hd, Wd, B, H, W, Cc, _launch())
+    _lib.check(rc, "spg_copy_grid_h16", dn)
+
+
 def patchify(x: torch.Tensor, cols: torch.Tensor) -> None:
     B, _, S, _ = x.shape
     lib, dn = _lib_for(cols)

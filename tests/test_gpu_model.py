@@ -151,6 +151,32 @@ def test_high_resolution_1024(model_fp16, spread_sd):
     assert _sig_err(out["edge"], ref["edge"]) <= MASK_TOL
 
 
+@pytest.mark.parametrize("size,batch", [(352, 2), (384, 1), (224, 1), (480, 1)])
+def test_other_resolutions_match_the_oracle(model_fp16, spread_sd, size, batch):
+    """Any S % 32 == 0 (models/feature_encoding.py:230-233), e.g. the 352 / 384 inputs common in COD work: the stage-3 /
+    stage-4 token grids (22 / 11 at 352) do not tile into 16 / 8 windows -> zero-padded windows in the trunk
+    (HF:modeling_sam2.py:395-399, incl. the query-pooling block), global attention over 484 tokens, and head convolutions
+    whose widths (44 / 88 / 176 / 352) take a ragged last tile column."""
+    from oracle.spegnet import spegnet_forward
+
+    x = _images(batch, size, seed=size)
+    ref = spegnet_forward(spread_sd, x)
+    with torch.no_grad():
+        out = model_fp16(x.cuda())
+    assert [tuple(p.shape) for p in out["predictions"]] == [(batch, 1, size // 4, size // 4), (batch, 1, size // 2, size // 2),
+                                                            (batch, 1, size, size)]
+    assert tuple(out["edge"].shape) == (batch, 1, size // 8, size // 8)
+    for i in range(3):
+        assert _sig_err(out["predictions"][i], ref["predictions"][i]) <= MASK_TOL, f"pred{i + 1}"
+    assert _sig_err(out["edge"], ref["edge"]) <= MASK_TOL
+    for key in ("context", "fused", "edge_features"):
+        a, b = out["features"][key].cpu(), ref["features"][key]
+        assert float((a - b).abs().max()) <= 5e-3 * float(b.abs().max()) + 1e-2, key
+    with torch.no_grad():  # batch invariance holds at these sizes too
+        single = model_fp16(x[:1].cuda())
+    assert torch.equal(single["predictions"][-1][0], out["predictions"][-1][0])
+
+
 def test_bf16_build_is_measured(model_bf16, spread_sd):
     """bf16 storage (7-bit mantissa) cannot meet 1e-2 on spread logits; its error is pinned here so that it
     neither regresses nor gets mistaken for the parity-grade build."""

@@ -292,7 +292,8 @@ def test_mask_stats_match_reference_quantisation_and_mae(ops, double_sigmoid):
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 8, 128, 64, 64), (1, 16, 256, 128, 64), (3, 5, 128, 64, 32),
-                                             (8, 64, 256, 128, 64)])
+                                             (8, 64, 256, 128, 64), (1, 12, 176, 128, 64), (2, 6, 96, 64, 64),
+                                             (1, 9, 192, 128, 64)])  # last three: ragged low-resolution rows
 def test_conv3x3_up2_matches_interpolate_then_conv(ops, B, H, W, Cin, Cout):
     """Fused bilinear x2 + 3x3 conv (+ folded bias, ReLU) against F.interpolate -> F.conv2d in fp32
     (models/object_detection.py:219,230-232); the last shape is large enough for the CTA-pair instance."""
@@ -543,3 +544,40 @@ def test_linear_resident_weights(ops, M, N, K, act):
     outf = torch.empty(M, N, device="cuda")
     ops.linear(a, w, outf, bias=bias, act=act)
     _close(outf, ref, 3e-4, 1e-4)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,head", [(2, 44, 44, 256, 64, True), (1, 88, 88, 320, 256, True), (1, 176, 176, 128, 128, False),
+                                                 (1, 48, 48, 64, 64, False), (2, 96, 96, 64, 128, True)])
+def test_conv3x3_ragged_widths(ops, B, H, W, Cin, Cout, head):
+    """Widths that neither divide 128 nor are multiples of it (the head at 352 / 384 inputs): 64- or 128-pixel tile
+    columns whose last one is ragged -- A rows beyond W are TMA zero fill, the NHWC store map clips them, the fused head
+    writes the compact map."""
+    g = torch.Generator(device="cuda").manual_seed(H + Cin)
+    x = _bf(torch.randn(B, H, W, Cin, device="cuda", generator=g))
+    w4 = _bf(torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / math.sqrt(9 * Cin))
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    wk = w4.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    out = _Guarded((B * H * W, Cout), H16)
+    hw = torch.randn(Cout, device="cuda", generator=g) if head else None
+    ho = _Guarded((B, 1, H, W), torch.float32) if head else None
+    ops.conv3x3(x, wk, out.view, bias=bias, act=ops.ACT_RELU, head_w=hw, head_b=-0.25, head_out=ho.view if head else None)
+    ref = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), w4.float(), bias, padding=1))
+    assert out.intact()
+    _close(out.view.view(B, H, W, Cout).permute(0, 3, 1, 2), ref, 2e-2, 1e-2)
+    if head:
+        assert ho.intact()
+        _close(ho.view, (ref * hw.view(1, -1, 1, 1)).sum(1, keepdim=True) - 0.25, 5e-3, 1e-3)
+        ho2 = torch.empty(B, 1, H, W, device="cuda")
+        ops.conv3x3(x, wk, None, bias=bias, act=ops.ACT_RELU, head_w=hw, head_b=-0.25, head_out=ho2)  # head only
+        assert torch.equal(ho2, ho.view)
+
+
+def test_copy_grid_pads_and_crops(ops):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    src = _bf(torch.randn(2, 22, 22, 576, device="cuda", generator=g))
+    dst = torch.zeros(2, 32, 32, 576, device="cuda", dtype=H16)
+    ops.copy_grid(src, dst, 22, 22)
+    assert torch.equal(dst[:, :22, :22], src) and float(dst[:, 22:].abs().max()) == 0 and float(dst[:, :, 22:].abs().max()) == 0
+    back = torch.empty_like(src)
+    ops.copy_grid(dst, back, 22, 22)
+    assert torch.equal(back, src)

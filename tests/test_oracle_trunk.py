@@ -21,6 +21,10 @@ def _hf_model(cfg: HieraConfig):
 @pytest.mark.parametrize("cfg,size", [
     (HieraConfig(), 256),                                                   # the real Hiera-L geometry
     (HieraConfig(stages=(1, 2, 3, 2), global_att_blocks=(4,)), 512),        # shallow, default resolution
+    # 352: the stage-3 / stage-4 token grids (22 / 11) do not tile into 16 / 8 windows -> padded windows (HF:395-399),
+    # incl. the query-pooling block at the stage change (window 16 on the 22 grid, pooled to 8 on the 11 grid)
+    (HieraConfig(stages=(1, 2, 4, 2), global_att_blocks=(5,)), 352),
+    (HieraConfig(stages=(1, 2, 3, 2), global_att_blocks=(4,)), 384),
 ])
 def test_trunk_matches_hf_port(cfg, size):
     torch.manual_seed(0)
