@@ -12,8 +12,10 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATHS = {"fp16": os.path.join(_HERE, "libspegnet_b200_fp16.so"),
-             "bf16": os.path.join(_HERE, "libspegnet_b200_bf16.so")}
+# SPEGNET_B200_LIBDIR: load the two libraries from another directory (same-box A/B of two builds; development only)
+_LIBDIR = os.environ.get("SPEGNET_B200_LIBDIR", _HERE)
+LIB_PATHS = {"fp16": os.path.join(_LIBDIR, "libspegnet_b200_fp16.so"),
+             "bf16": os.path.join(_LIBDIR, "libspegnet_b200_bf16.so")}
 DEFAULT_DTYPE = "fp16"
 
 SPG_OK = 0

@@ -88,7 +88,7 @@ struct GemmArgs {
     // row band (tiles_x * tile_w >= W), tiles_img = tiles_x * H / tile_h tiles an image.  `ragged` (W % tile_w != 0): the
     // pixels with x >= W of the last tile column do not exist -- their A rows are TMA zero fill, their outputs are
     // clipped by a 4-D store map / skipped by the fused head.
-    int tiles_x, tiles_img, ragged;
+    int tiles_x, tiles_img, ragged, tile_h;
     // fused bilinear x2 upsample (kUp2 instances): the conv runs on the LOW-resolution grid with 4 output phases stacked
     // along N; w holds one [N, K] weight set per row class (top / interior / bottom image row), corr the pre-activation
     // corrections of the first / last image column, the store is a pixel shuffle (see spg_conv3x3_up2_h16)
@@ -273,7 +273,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     img = m_blk / p.tiles_img;
                     const int rem = m_blk - img * p.tiles_img;
                     const int ty = rem / p.tiles_x;
-                    y0 = ty * (kBlockM / p.tile_w);
+                    y0 = ty * p.tile_h;
                     x0 = (rem - ty * p.tiles_x) * p.tile_w;
                 }
                 // The first touch of an m-block's A rows comes from HBM (the weights and every later n-tile hit L2), and the
@@ -509,12 +509,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const float* corr_row = nullptr;
             // conv modes: image / row / column of this warp's 32 pixels (they lie in one image row: tile_w >= 32)
             int cv_img = 0, cv_y = 0, cv_x = 0;
-            if (p.conv) {
+            // (exact tilings address their outputs by the flat pixel index `row`; ragged convolutions run the generic
+            // instance, so that the specialised ones carry none of this)
+            constexpr bool kGenericInst = kAct < 0;
+            if (kUp2 || (kGenericInst && p.ragged)) {
                 cv_img = m_blk / p.tiles_img;
                 const int rem = m_blk - cv_img * p.tiles_img;
                 const int ty = rem / p.tiles_x;
                 const int pix0 = quarter * 32;
-                cv_y = ty * (kBlockM / p.tile_w) + pix0 / p.tile_w;
+                cv_y = ty * p.tile_h + pix0 / p.tile_w;
                 cv_x = (rem - ty * p.tiles_x) * p.tile_w + pix0 % p.tile_w;
             }
             if (kUp2) {
@@ -706,7 +709,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                 const int phase = n / p.cout;  // (row phase, column phase) = (phase >> 1, phase & 1)
                                 tma_store_5d(&tmap_out, my_staging + slot * p.buf_bytes, n - phase * p.cout, phase & 1, up_x,
                                              phase >> 1, up_img_row);
-                            } else if (p.ragged) {  // [C, W, H, B] map: columns x >= W of the last tile column are clipped
+                            } else if (kAct < 0 && p.ragged) {  // [C, W, H, B] map: columns x >= W of the last tile column are clipped
                                 tma_store_4d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, cv_x, cv_y, cv_img);
                             } else {
                                 tma_store_2d(&tmap_out, my_staging + slot * p.buf_bytes, n0 + c_first * 16, row0);
@@ -831,7 +834,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (part == 0 && row_ok) {
 #pragma unroll
                     for (int k = 1; k < kParts; ++k) head_acc += headp_s[(k - 1) * 128 + row_in_tile];
-                    if (!p.ragged) p.head_out[row] = head_acc + p.head_b;
+                    if (!(kAct < 0 && p.ragged)) p.head_out[row] = head_acc + p.head_b;
                     else if (cv_x + lane < p.W)  // head_out is the compact [B, H, W] map
                         p.head_out[(static_cast<size_t>(cv_img) * p.H + cv_y) * p.W + cv_x + lane] = head_acc + p.head_b;
                 }
@@ -1030,6 +1033,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     } else if (a.up2) {
         if (pair) SPG_LAUNCH_ONE_UP2(1);
         else SPG_LAUNCH_ONE_UP2(0);
+    } else if (a.ragged) {  // ragged conv tile columns: only the generic instance carries the clipping code
+        SPG_LAUNCH(-1, -1, -1, -1, -1, kEpiWarpsDefault);
     } else if (a.act == SPG_ACT_NONE && !a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH_EW(SPG_ACT_NONE, 0, 0, 0, 1);
     else if (a.act == SPG_ACT_NONE && a.out_f32 && a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 1, 0, 1, kEpiWarpsDefault);
     else if (a.act == SPG_ACT_NONE && a.out_f32 && !a.has_res && !head && a.has_out) SPG_LAUNCH(SPG_ACT_NONE, 1, 0, 0, 1, kEpiWarpsDefault);
@@ -1201,6 +1206,7 @@ extern "C" int spg_conv3x3_h16(const void* x, const void* w, int B, int H, int W
     GemmArgs a{};
     EpiMaps em;
     a.tiles_x = (W + tile_w - 1) / tile_w;
+    a.tile_h = tile_h;
     a.tiles_img = a.tiles_x * (H / tile_h);
     a.ragged = W % tile_w != 0 ? 1 : 0;
     SPG_CHECK_ARG(!a.ragged || tile_w >= 32, "ragged conv tiles need >= 32 pixels per row");
@@ -1251,6 +1257,7 @@ extern "C" int spg_conv3x3_up2_h16(const void* x, const void* w_phase, const flo
     GemmArgs a{};
     EpiMaps em;
     a.tiles_x = (W + kBlockM - 1) / kBlockM;
+    a.tile_h = 1;
     a.tiles_img = a.tiles_x * H;
     a.ragged = W % kBlockM != 0 ? 1 : 0;  // the pixel-shuffle store map clips x >= W by itself
     a.num_m_tiles = B * a.tiles_img;
