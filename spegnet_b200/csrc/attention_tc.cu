@@ -30,7 +30,8 @@ namespace {
 constexpr int kHd = 72;
 constexpr int kWs = 16;                 // window edge
 constexpr int kKeys = kWs * kWs;        // 256
-constexpr int kThreadsTc = 320;  // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9 softmax of query tile 0 / 1
+constexpr int kThreadsTc = 320;  // global kernel: warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9 softmax of query tile 0 / 1
+constexpr int kThreadsWin = 352; // windowed kernel: + warp 10 = the MMA issuer of query tile 1 (warp 1 serves tile 0)
 constexpr uint32_t kQMain = 128 * 128;  // one 128-query tile, dims 0..63   (SWIZZLE_128B rows of 128 B)
 constexpr uint32_t kQTail = 128 * 32;   // dims 64..79                      (SWIZZLE_32B rows of 32 B)
 constexpr uint32_t kKMain = kKeys * 128, kKTail = kKeys * 32;
@@ -45,6 +46,48 @@ constexpr uint32_t kOffVt = kOffV + kKMain;
 constexpr uint32_t kOffBar = kOffVt + kKTail;         // 204800
 constexpr uint32_t kSmemTc = kOffBar + 256 + 1024;    // + barriers + alignment slack
 
+// Softmax arithmetic on Blackwell's packed / 3-input fp32 forms (same roundings as the scalar code they replace, so the
+// results are bit-identical): FMNMX3 halves the instructions and the dependent chain of the row maximum, FFMA2 / FADD2
+// process two probabilities per issue slot -- the softmax warps are the busy resource of these kernels.
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// 32 raw fp32 scores -> running maxima (two independent chains)
+__device__ __forceinline__ void row_max32(const uint32_t (&raw)[32], float& m0, float& m1) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        m0 = max3(m0, __uint_as_float(raw[i]), __uint_as_float(raw[i + 1]));
+        m1 = max3(m1, __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+    }
+}
+// {p0, p1} = 2^({s0, s1} * scale - m); sum2 += {p0, p1} (packed); returns the 16-bit pair
+__device__ __forceinline__ uint32_t exp2_pair(uint32_t s0, uint32_t s1, unsigned long long scale2, unsigned long long negm2,
+                                              unsigned long long& sum2) {
+    unsigned long long x, t;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(s0), "r"(s1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(x), "l"(scale2), "l"(negm2));
+    float t0, t1, p0, p1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(t0), "=f"(t1) : "l"(t));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(t0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(t1));
+    unsigned long long pp;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(pp) : "f"(p0), "f"(p1));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum2) : "l"(sum2), "l"(pp));
+    return pack2(p0, p1);
+}
+__device__ __forceinline__ unsigned long long splat2(float v) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float hsum2(unsigned long long v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a + b;
+}
+
 struct AttnTcParams {
     h16* out;  // [B*H*W, D]
     int B, H, W, D, heads;
@@ -54,7 +97,7 @@ struct AttnTcParams {
     float scale_log2e;
 };
 
-__global__ void __launch_bounds__(kThreadsTc, 1)
+__global__ void __launch_bounds__(kThreadsWin, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_constant__ CUtensorMap tmap_tail,
                     const AttnTcParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -71,10 +114,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
         tma_prefetch_desc(&tmap_tail);
         for (int s = 0; s < 2; ++s) {
             mbar_init(qk_full + 8 * s, 1);
-            mbar_init(qk_empty + 8 * s, 1);
+            mbar_init(qk_empty + 8 * s, 2);  // one commit per MMA issuer (query tile)
         }
         mbar_init(v_full, 1);
-        mbar_init(v_empty, 1);
+        mbar_init(v_empty, 2);
         for (int r = 0; r < 2; ++r) {
             mbar_init(s_full + 8 * r, 1);
             mbar_init(p_full + 8 * r, 4);       // one arrive per softmax warp of the region's warpgroup
@@ -133,9 +176,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 || warp == 10) {
+        // ===================== MMA issuers: warp 1 serves query tile / TMEM region 0, warp 10 region 1 =====================
+        // Each region is its own chain S -> softmax -> PV -> epilogue -> next S, and the chain's latency is the kernel's
+        // time (ncu: the softmax warps wait on s_full / o_full for half of their cycles).  With ONE issuing thread a
+        // region's ready step queued behind the other region's 32-MMA PV issue; one issuer per region answers at once.
+        // tcgen05.commit tracks the issuing thread's own MMAs, so the shared Q/K and V buffers are released by one
+        // commit from each issuer (barrier count 2).
         if (lane == 0) {
+            const int r = warp == 1 ? 0 : 1;
 #ifdef SPG_FP16
             constexpr uint32_t kFmt = 0u;
 #else
@@ -145,15 +194,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
             constexpr uint32_t idesc_s = kIdescBase | ((256u >> 3) << 17);                      // K-major A and B
             constexpr uint32_t idesc_pv64 = kIdescBase | (1u << 16) | ((64u >> 3) << 17);       // B MN-major
             constexpr uint32_t idesc_pv16 = kIdescBase | (1u << 16) | ((16u >> 3) << 17);
-            // Event-driven issue: each TMEM region runs its own state machine (need S -> need PV -> next item) and the
-            // single MMA thread polls both with non-blocking barrier probes, issuing whichever step has its inputs
-            // ready.  A fixed issue order with blocking waits would hold one region's ready step behind the other
-            // region's barrier (measured: the softmax warps then idle ~40 % of the time on s_full / o_full).
-            auto issue_s = [&](int n, int r) {
+            const uint32_t d = tmem_base + 256u * r;
+            int n = 0;
+            for (int item = blockIdx.x; item < p.items; item += gridDim.x, ++n) {
                 const uint32_t st = base + (n & 1) * kStageQK;
-                tc_fence_after();
-                const uint32_t d = tmem_base + 256u * r;
                 const uint32_t qm = st + kOffQ + r * kQMain, qt = st + kOffQt + r * kQTail;
+                mbar_wait(qk_full + 8 * (n & 1), (n >> 1) & 1);
+                mbar_wait(region_free + 8 * r, (n & 1) ^ 1u);
+                tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_bf16_ss(d, make_smem_desc(qm + 32u * k, 2, 1024, 16),
@@ -161,10 +209,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
                 // dims 64..79 from the 32B-swizzled tails (72..79 are TMA zero fill)
                 umma_bf16_ss(d, make_smem_desc(qt, 6, 256, 16), make_smem_desc(st + kOffKt, 6, 256, 16), idesc_s, 1);
                 umma_commit(s_full + 8 * r);
-            };
-            auto issue_pv = [&](int r) {
+                umma_commit(qk_empty + 8 * (n & 1));  // this tile's share of "Q / K of item n consumed"
+                mbar_wait(v_full, n & 1);
+                mbar_wait(p_full + 8 * r, n & 1);
                 tc_fence_after();
-                const uint32_t d = tmem_base + 256u * r;
 #pragma unroll 4
                 for (int k = 0; k < kKeys / 16; ++k) {
                     const uint32_t a_tmem = d + 8u * k;  // 16 keys = 8 packed fp16-pair columns of P
@@ -172,48 +220,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
                     umma_ts(d + 192, a_tmem, make_smem_desc(base + kOffVt + 512u * k, 6, 256, 16), idesc_pv16, k != 0);
                 }
                 umma_commit(o_full + 8 * r);
-            };
-            const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-            int item_of[2] = {0, 0};      // next work item (CTA-local index) of each region
-            int need_pv[2] = {0, 0};      // 0: S not issued yet for item_of[r]; 1: S issued, PV pending
-            int s_count[2] = {0, 0};      // S steps issued per Q/K stage (both regions -> stage can be released)
-            int pv_count = 0;             // PV steps issued for the current V buffer
-            uint32_t spins = 0;
-            while (item_of[0] < my_items || item_of[1] < my_items) {
-                bool progressed = false;
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int n = item_of[r];
-                    if (n >= my_items) continue;
-                    if (!need_pv[r]) {
-                        if (mbar_test(qk_full + 8 * (n & 1), (n >> 1) & 1) && mbar_test(region_free + 8 * r, (n & 1) ^ 1u)) {
-                            issue_s(n, r);
-                            if (++s_count[n & 1] == 2) {
-                                s_count[n & 1] = 0;
-                                umma_commit(qk_empty + 8 * (n & 1));  // Q / K of item n consumed by both tiles
-                            }
-                            need_pv[r] = 1;
-                            progressed = true;
-                        }
-                    } else {
-                        if (mbar_test(v_full, n & 1) && mbar_test(p_full + 8 * r, n & 1)) {
-                            issue_pv(r);
-                            if (++pv_count == 2) {
-                                pv_count = 0;
-                                umma_commit(v_empty);  // V of item n consumed by both tiles
-                            }
-                            need_pv[r] = 0;
-                            item_of[r] = n + 1;
-                            progressed = true;
-                        }
-                    }
-                }
-                if (progressed) {
-                    spins = 0;
-                } else if (++spins > (1u << 26)) {
-                    printf("spg: attention_tc MMA issuer stuck block=%d items=(%d,%d)\n", (int)blockIdx.x, item_of[0], item_of[1]);
-                    __trap();
-                }
+                umma_commit(v_empty);  // this tile's share of "V of item n consumed"
             }
         }
     } else {
@@ -231,33 +238,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
             tc_fence_after();
             uint32_t ra[32], rb[32];
             // ---- pass 1: row maximum (32-column TMEM loads, double-buffered against the reductions)
-            float mx = -INFINITY;
+            float mx0 = -INFINITY, mx1 = -INFINITY;
             tmem_ld32(lane_addr, ra);
 #pragma unroll 1
             for (int c = 0; c < kKeys / 32; c += 2) {
                 tmem_ld_wait();
                 tmem_ld32(lane_addr + 32 * (c + 1), rb);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
+                row_max32(ra, mx0, mx1);
                 tmem_ld_wait();
                 if (c + 2 < kKeys / 32) tmem_ld32(lane_addr + 32 * (c + 2), ra);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
+                row_max32(rb, mx0, mx1);
             }
-            const float m = mx * p.scale_log2e;
+            const float m = fmaxf(mx0, mx1) * p.scale_log2e;
             // ---- pass 2: p = 2^(s * scale - m), row sum, pack to 16 bit, write back over the consumed columns
-            float sum0 = 0.f, sum1 = 0.f;
+            unsigned long long sum2 = 0ull;  // {sum of even keys, sum of odd keys}
+            const unsigned long long scale2 = splat2(p.scale_log2e), negm2 = splat2(-m);
             auto exp_pack_store = [&](const uint32_t (&raw)[32], int c) {
                 uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0, p1;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2e, -m)));
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2e, -m)));
-                    sum0 += p0;
-                    sum1 += p1;
-                    pk[i] = pack2(p0, p1);
-                }
+                for (int i = 0; i < 16; ++i) pk[i] = exp2_pair(raw[2 * i], raw[2 * i + 1], scale2, negm2, sum2);
                 tmem_st16(lane_addr + 16 * c, pk);
             };
             tmem_ld32(lane_addr, ra);
@@ -270,7 +269,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
                 if (c + 2 < kKeys / 32) tmem_ld32(lane_addr + 32 * (c + 2), ra);
                 exp_pack_store(rb, c + 1);
             }
-            const float sum = sum0 + sum1;
+            const float sum = hsum2(sum2);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -282,22 +281,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
             mbar_wait(o_full + 8 * r, par);
             tc_fence_after();
             const float inv = 1.f / sum;
+            // the whole O row moves to registers first and the region is handed back at once: the next item's S MMAs
+            // run while this thread scales, packs and stores
+            uint32_t o[5][16];
+#pragma unroll
+            for (int c = 0; c < 5; ++c) tmem_ld16(lane_addr + 128 + 16 * c, o[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(region_free + 8 * r);
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
-                uint32_t raw[16];
-                tmem_ld16(lane_addr + 128 + 16 * c, raw);
-                tmem_ld_wait();
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * inv;
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(o[c][i]) * inv;
                 dst[2 * c] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
                 if (c < 4)  // dims 72..79 of the last chunk are padding
                     dst[2 * c + 1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]),
                                                 pack2(v[14], v[15]));
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(region_free + 8 * r);
         }
     }
 
@@ -582,7 +584,7 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
             decode(item, head, img_row0, qtile0);
             uint32_t ra[32], rb[32];
             // ---- pass A: running maximum of the raw scores over all key blocks
-            float mx = -INFINITY;
+            float mx0 = -INFINITY, mx1 = -INFINITY;
             for (int j = 0; j < nkb; j += 2) {  // 256 keys per handshake
                 mbar_wait(s_full + 8 * r, s_cnt & 1u);
                 ++s_cnt;
@@ -592,27 +594,21 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
                     tmem_ld32(lane_addr + c, ra);
                     tmem_ld32(lane_addr + c + 32, rb);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+                    row_max32(ra, mx0, mx1);
+                    row_max32(rb, mx0, mx1);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sa_free + 8 * r);
             }
-            const float m = mx * p.scale_log2e;
+            const float m = fmaxf(mx0, mx1) * p.scale_log2e;
             // ---- pass B: probabilities of every key block, packed in place; O accumulates in TMEM
-            float sum0 = 0.f, sum1 = 0.f;
+            unsigned long long sum2 = 0ull;  // {sum of even keys, sum of odd keys}
+            const unsigned long long scale2 = splat2(p.scale_log2e), negm2 = splat2(-m);
             auto exp_pack_store = [&](const uint32_t (&raw)[32], int c) {
                 uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float p0, p1;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(__uint_as_float(raw[2 * i]), p.scale_log2e, -m)));
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(__uint_as_float(raw[2 * i + 1]), p.scale_log2e, -m)));
-                    sum0 += p0;
-                    sum1 += p1;
-                    pk[i] = pack2(p0, p1);
-                }
+                for (int i = 0; i < 16; ++i) pk[i] = exp2_pair(raw[2 * i], raw[2 * i + 1], scale2, negm2, sum2);
                 tmem_st16(lane_addr + 16 * c, pk);
             };
             for (int j = 0; j < nkb; ++j) {
@@ -641,7 +637,7 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
             uint4* dst = reinterpret_cast<uint4*>(p.out + tok * p.D + head * kHd);
             mbar_wait(pv_done + 8 * r, n & 1u);
             tc_fence_after();
-            const float inv = 1.f / (sum0 + sum1);
+            const float inv = 1.f / (hsum2(sum2));
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
                 uint32_t raw[16];
@@ -718,7 +714,7 @@ extern "C" int spg_window_attention_tc_h16(const void* qkv, void* out, int B, in
         attr_set.done();
     }
     const int grid = p.items < sm_count() ? p.items : sm_count();
-    SPG_CHECK_CUDA((launch_pdl(attention_tc_kernel, grid, kThreadsTc, kSmemTc, LaunchCtx(launch), tmain, ttail, p)));
+    SPG_CHECK_CUDA((launch_pdl(attention_tc_kernel, grid, kThreadsWin, kSmemTc, LaunchCtx(launch), tmain, ttail, p)));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     SPG_CHECK_LAUNCH();
     return SPG_OK;

@@ -50,7 +50,13 @@ constexpr int kAccStageCols = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kBarBytes = 1024;                                // pipeline barriers + residual barriers
-constexpr int kEpiScratch = (2 * 256 + 256 + 3 * 128 + 2 * 256 + 2 * 256) * 4;  // bias[2][256], head weights[256], head partials[3][128], LN column sums / gamma[2][256], LN beta[2][256]
+// Epilogue scratch, sized per launch in whole KB (every shared-memory piece is a 1 KB multiple, so nothing is lost to
+// alignment and the operand ring gets what is left): bias[2][256] | LayerNorm modes: column sums or gamma [2][256],
+// beta [2][256] | fused head: weights[256], partials[3][128]
+constexpr int kScratchBias = 2 * 256 * 4;
+constexpr int kScratchLn = 4 * 256 * 4;
+constexpr int kScratchHead = 3 * 1024;
+inline int epi_scratch_bytes(int ln_mode, bool head) { return kScratchBias + (ln_mode ? kScratchLn : 0) + (head ? kScratchHead : 0); }
 constexpr int kLnRec = 32;                                      // floats per LayerNorm row record {c, P, (s1, s2) x P}
 constexpr int kLnBufBytes = 32 * 32;                            // staging buffer of the 16-bit centred copy: 32 rows x 16 columns
 // LayerNorm applied by the producer (kLn == 3): staging ring of the normalised 16-bit rows per epilogue warp, and the
@@ -81,6 +87,12 @@ struct GemmArgs {
     // per TMA round trip instead of 1.3 -- these GEMMs are bound by that round trip, not by the tensor pipe
     int b_resident;
     int b_res_tiles;  // weight tiles held resident: k-chunks (linear) or 9 taps x channel chunks (row-halo conv)
+    // ln_mode 3 (the CTAs / pairs of a cluster work on the n-tiles of ONE row block at the same time): every A chunk is
+    // fetched from L2 by one CTA of the cluster and TMA-multicast to the CTAs that need the same rows (k-chunk kc by
+    // cluster position kc mod #n-tiles): the L2 -> SM traffic of A drops by #n-tiles.  A stage is then released by the
+    // MMA issuers of ALL n-tiles (commit multicast to every CTA of the cluster).
+    int a_mcast;
+    int scratch_bytes;  // epilogue scratch of this launch (epi_scratch_bytes)
     // conv mode
     int conv;
     int H, W, cin_chunks, tile_w;
@@ -197,7 +209,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     auto res_bar = [&](int ew, int slot) { return bar_addr + 256u + 8u * (ew * kResSlots + slot); };
     auto ln_bar = [&](int b) { return bar_addr + 768u + 8u * b; };  // kLn == 3: statistics of tile parity b have arrived
     const uint32_t scratch_addr = bar_addr + kBarBytes;
-    const uint32_t staging_addr = (scratch_addr + kEpiScratch + 1023u) & ~1023u;  // 128B-swizzle atoms: 1 KB aligned
+    const uint32_t staging_addr = (scratch_addr + static_cast<uint32_t>(p.scratch_bytes) + 1023u) & ~1023u;  // 128B-swizzle atoms: 1 KB aligned
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -214,7 +226,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (kLn == 2) tma_prefetch_desc(&tmap_ln);
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), (kLn == 3 && p.a_mcast) ? static_cast<uint32_t>(p.num_n_tiles) : 1u);
         }
         mbar_init(b_res_bar, 1);
         for (int a = 0; a < 2; ++a) {
@@ -252,6 +264,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             // pair mode: both CTAs load; all transaction bytes are signalled on the leader's full barrier
             const uint32_t n_half = kPair ? rank * (p.block_n / 2) : 0u;  // this CTA's slice of the weight tile
+            // a_mcast: position of this CTA (pair) among the n-tiles of the cluster, and the CTAs that share its A rows
+            const bool mcast = kLn == 3 && p.a_mcast != 0;
+            const int cpos = static_cast<int>(kPair ? crank >> 1 : crank);
+            uint16_t a_mask = 0;
+            for (int q = 0; q < p.num_n_tiles; ++q) a_mask |= static_cast<uint16_t>(1u << (kPair ? 2 * q + static_cast<int>(rank) : q));
+            int a_turn = 0;  // k-chunk counter mod #n-tiles (runs across tiles: whole chunks, any K)
             [[maybe_unused]] int trace_i = 0;
             if (p.b_resident && unit < total_tiles) {
                 // this CTA's n-block never changes (grid % n-tiles == 0): load its weight tile once
@@ -337,6 +355,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         const int dx = tap - (tap / 3) * 3 - 1;
                         if (kPair) tma_load_4d_pair(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 + dx, y0 + dy, img);
                         else tma_load_4d(a_dst, &tmap_a, full_bar(stage), cc * kBlockK, x0 + dx, y0 + dy, img);
+                    } else if (mcast) {
+                        if (a_turn == cpos) {
+                            if (kPair) tma_load_2d_pair_mcast(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM, a_mask);
+                            else tma_load_2d_mcast(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM, a_mask);
+                        }
+                        if (++a_turn == p.num_n_tiles) a_turn = 0;
                     } else {
                         if (kPair) tma_load_2d_pair(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
                         else tma_load_2d(a_dst, &tmap_a, full_bar(stage), kc * kBlockK, m_blk * kBlockM);
@@ -362,6 +386,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             auto commit = [&](uint32_t bar) {
                 if (kPair) umma_commit_pair(bar, static_cast<uint16_t>(3u << (crank & ~1u)));
                 else umma_commit(bar);
+            };
+            // a_mcast: the stage is shared by the whole cluster -- release it on every CTA's empty barrier
+            const bool mcast = kLn == 3 && p.a_mcast != 0;
+            const uint16_t all_mask = static_cast<uint16_t>((1u << ((kPair ? 2 : 1) * p.num_n_tiles)) - 1u);
+            auto release = [&](uint32_t bar) {
+                if (!mcast) commit(bar);
+                else if (kPair) umma_commit_pair(bar, all_mask);
+                else umma_commit_mcast(bar, all_mask);
             };
             int stage = 0;
             uint32_t phase = 0;
@@ -425,7 +457,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                             mma(d_tmem, a_desc + koff, b_desc + koff, (kc | k) != 0);
                         }
                     }
-                    commit(empty_bar(stage));
+                    release(empty_bar(stage));
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1u;
@@ -450,10 +482,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int etid = threadIdx.x - 64;
         const int row_in_tile = quarter * 32 + lane;
         float* bias_s = reinterpret_cast<float*>(smem_raw + (scratch_addr - raw_addr));
-        float* headw_s = bias_s + 2 * 256;
-        float* headp_s = headw_s + 256;
-        float* cw_s = headp_s + 3 * 128;  // [2][256] column sums of W' (kLn == 1) / LayerNorm gamma (kLn == 3)
+        float* cw_s = bias_s + 2 * 256;   // [2][256] column sums of W' (kLn == 1) / LayerNorm gamma (kLn == 3)
         float* lnb_s = cw_s + 2 * 256;    // [2][256] LayerNorm beta (kLn == 3)
+        float* headw_s = bias_s + 2 * 256 + (p.ln_mode ? 4 * 256 : 0);  // fused head (see epi_scratch_bytes)
+        float* headp_s = headw_s + 256;
         const uint32_t my_staging = staging_addr + ewarp * kResSlots * p.buf_bytes;
         // kLn == 2: ring of 1 KB buffers for the 16-bit centred copy, slot-locked to the main ring
         const uint32_t my_ln_staging = staging_addr + kEpiWarps * kResSlots * p.buf_bytes + ewarp * kResSlots * kLnBufBytes;
@@ -914,17 +946,24 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const EpiMaps& em,
     const int staging_all = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
                             (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0) +
                             (a.ln_mode == 3 ? a.epi_warps * kLnSlots * kLnBufBytes + kLnXBytes : 0);
+    a.scratch_bytes = epi_scratch_bytes(a.ln_mode, a.head_w != nullptr);
+    // 1024: the dynamic shared memory base is only 16 B aligned by contract; everything after it is a 1 KB multiple
+    const int fixed_base = 1024 + kBarBytes + a.scratch_bytes + ((bn_cta * 128) % 1024 ? 1024 : 0);
     if (a.b_resident && !a.halo &&
-        kSmemBudget - (1024 + kBarBytes + kEpiScratch + 1024 + staging_all) - a.num_k_chunks * bn_cta * 128 < 4 * kAStageBytes)
+        kSmemBudget - (fixed_base + staging_all) - a.num_k_chunks * bn_cta * 128 < 4 * kAStageBytes)
         a.b_resident = 0;  // the resident weight tile would leave fewer than four A stages
     a.b_res_tiles = a.b_resident ? (a.halo ? 9 * a.cin_chunks : a.num_k_chunks) : 0;
+    // off by default: built and correct (tests/test_gpu_modes.py runs the LayerNorm-producer tests with it on), but the
+    // step is power-capped, not L2-feed bound -- same-box A/B 1006.4 (on) vs 1006.5 img/s (off), DESIGN.md 4.1b2
+    static const int amcast_env = [] { const char* e = getenv("SPG_GEMM_AMCAST"); return e ? atoi(e) : 0; }();
+    a.a_mcast = (amcast_env && a.ln_mode == 3 && a.num_n_tiles > 1 && !a.b_resident && !a.conv) ? 1 : 0;
     const int b_res_bytes = a.b_res_tiles * bn_cta * 128;
     const int stage_bytes = a.b_resident ? (a.halo ? kHaloABytes : kAStageBytes)
                                          : (a.halo ? kHaloABytes + 3 * bn_cta * 128 : kAStageBytes + bn_cta * 128);
     const int staging = (a.has_out ? a.epi_warps * kResSlots * a.buf_bytes : 0) +
                         (a.ln_mode == 2 ? a.epi_warps * kResSlots * kLnBufBytes : 0) +
                         (a.ln_mode == 3 ? a.epi_warps * kLnSlots * kLnBufBytes + kLnXBytes : 0);
-    const int fixed = 1024 + kBarBytes + kEpiScratch + 1024 + staging + b_res_bytes;
+    const int fixed = fixed_base + staging + b_res_bytes;
     int stages = (kSmemBudget - fixed) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (!a.b_resident && stages > a.num_k_chunks + 1) stages = a.num_k_chunks + 1;  // no point in a deeper ring

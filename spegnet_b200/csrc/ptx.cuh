@@ -113,6 +113,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
         : "memory");
 }
 
+// Multicast form: the box lands at the same CTA-relative offset in every CTA of `cta_mask` (cluster ranks) and each
+// destination's mbarrier at the CTA-relative offset of `bar` receives the transaction bytes.
+__device__ __forceinline__ void tma_load_2d_mcast(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0,
+                                                  int32_t c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar,
                                             int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
     asm volatile(
@@ -203,6 +215,13 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+
+// the arrive is delivered to the mbarrier at this CTA-relative offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
                  : "memory");
 }
 
@@ -333,6 +352,16 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
         " [%0], [%1, {%3, %4}], [%2];"
         :
         : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+// multicast from a CTA of a pair to the same-rank CTAs of other pairs: every destination signals ITS pair leader
+__device__ __forceinline__ void tma_load_2d_pair_mcast(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0,
+                                                       int32_t c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "h"(cta_mask)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* m, uint32_t bar, int32_t c0,
