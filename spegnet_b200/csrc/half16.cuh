@@ -79,4 +79,42 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE operations per issue slot, same roundings as the
+// scalar forms).  A pair lives in a 64-bit register.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_split(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// one 16-byte vector of 8 halves <-> four fp32 pairs
+__device__ __forceinline__ void unpack8_f2(const uint4& u, f32x2 (&f)[4]) {
+    f[0] = f2_make(h_lo(u.x), h_hi(u.x));
+    f[1] = f2_make(h_lo(u.y), h_hi(u.y));
+    f[2] = f2_make(h_lo(u.z), h_hi(u.z));
+    f[3] = f2_make(h_lo(u.w), h_hi(u.w));
+}
+__device__ __forceinline__ uint32_t pack_f2(f32x2 v) {
+    float lo, hi;
+    f2_split(v, lo, hi);
+    return pack2(lo, hi);
+}
+__device__ __forceinline__ uint4 pack8_f2(const f32x2 (&f)[4]) { return make_uint4(pack_f2(f[0]), pack_f2(f[1]), pack_f2(f[2]), pack_f2(f[3])); }
+
 }  // namespace spg

@@ -205,9 +205,34 @@ def test_upsample_concat(ops):
     _close(out2, up(a).permute(0, 2, 3, 1), 1e-2, 1e-2)
 
 
-def test_fusion_combine_se_scale(ops):
-    g = torch.Generator(device="cuda").manual_seed(9)
-    B, Hs, C = 2, 16, 512
+@pytest.mark.parametrize("h0,w0,c0,h1,w1,c1,Ho,Wo", [
+    (16, 16, 256, 16, 16, 64, 32, 32),   # decoder stage 1: both sources x2 (constant-tap kernel)
+    (16, 24, 128, 8, 12, 64, 32, 48),    # stage 2 ratios (x2 + x4) on a non-square grid
+    (8, 8, 64, 8, 8, 8, 16, 16),         # smallest grid: every pixel is a border pixel of the 3x3 / 2x2 patches
+    (8, 8, 64, 16, 16, 32, 32, 32),      # src0 x4: generic kernel
+    (4, 6, 32, 0, 0, 0, 12, 18),         # x3, no second source: generic kernel
+])
+def test_upsample_concat_ratios(ops, h0, w0, c0, h1, w1, c1, Ho, Wo):
+    """Every pixel (borders included) of both kernels against ATen's bilinear on the same 16-bit inputs: the result is
+    the 16-bit rounding of an fp32 interpolation, so it may differ from the rounded reference by one ulp at most."""
+    if Ho % 2 or Wo % 2:
+        pytest.skip("even outputs only")
+    g = torch.Generator(device="cuda").manual_seed(h0 * 7 + Wo)
+    a = _bf(torch.randn(2, h0, w0, c0, device="cuda", generator=g))
+    e = _bf(torch.randn(2, h1, w1, c1, device="cuda", generator=g)) if c1 else None
+    out = torch.full((2, Ho, Wo, c0 + c1), float("nan"), device="cuda", dtype=H16)
+    ops.upsample_concat(a, e, out)
+    up = lambda t: F.interpolate(t.float().permute(0, 3, 1, 2), size=(Ho, Wo), mode="bilinear", align_corners=False)  # noqa: E731
+    ref = torch.cat([up(a)] + ([up(e)] if c1 else []), 1).permute(0, 2, 3, 1)
+    ulp = 2.0 ** -10 if H16 == torch.float16 else 2.0 ** -7
+    err = (out.float() - ref).abs()
+    assert bool((err <= ulp * ref.abs().clamp_min(2.0 ** -14) * 1.01 + 1e-7).all()), f"max err {err.max().item():.3e}"
+
+
+@pytest.mark.parametrize("Hs", [16, 8, 4, 64])
+def test_fusion_combine_se_scale(ops, Hs):
+    g = torch.Generator(device="cuda").manual_seed(9 + Hs)
+    B, C = 2, 512
     g2 = torch.randn(B, Hs, Hs, C, device="cuda", generator=g)
     g3 = torch.randn(B, Hs // 2, Hs // 2, C, device="cuda", generator=g)
     g4 = torch.randn(B, Hs // 4, Hs // 4, C, device="cuda", generator=g)
