@@ -61,7 +61,7 @@ class ClockSampler:
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
@@ -92,7 +92,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        clocks, maxes, reasons = [], [], set()
+        clocks, maxes, reasons, power, limit = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 8:
@@ -105,8 +105,14 @@ class ClockSampler:
             for name, v in zip(names, r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+            try:  # board power: the step runs against the power cap ("what bounds the step")
+                power.append(float(r[3]))
+                limit.append(float(r[8]))
+            except (ValueError, IndexError):
+                pass
         return {"sm_mhz": statistics.median(clocks) if clocks else None,
-                "sm_max_mhz": max(maxes) if maxes else None, "reasons": sorted(reasons), "samples": len(clocks)}
+                "sm_max_mhz": max(maxes) if maxes else None, "reasons": sorted(reasons), "samples": len(clocks),
+                "power_w": statistics.median(power) if power else None, "power_limit_w": max(limit) if limit else None}
 
 
 def cpu_reference_rate(state_dict, size: int, budget_s: float, max_images: int):
