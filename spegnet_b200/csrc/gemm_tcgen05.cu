@@ -1212,6 +1212,10 @@ extern "C" int spg_linear_h16(const void* A, const void* W, int M, int N, int K,
     a.tile_w = 1;
     if (int rc = fill_epilogue(a, em, ep, M, N)) return rc;
     decide_pair(a);
+    // LayerNorm clusters: 3 n-tiles x CTA pairs = 6-CTA clusters, of which a B200 holds 22 (132 of 148 SMs); without
+    // pairs the clusters are 3 CTAs and 46 fit (138 SMs).  SPG_LN_PAIR=0 selects that (experiment knob)
+    static const int ln_pair_env = [] { const char* e = getenv("SPG_LN_PAIR"); return e ? atoi(e) : 1; }();
+    if (a.ln_mode == 3 && !ln_pair_env) a.pair = 0;
     // resident weights: short K, plain tiling (N a multiple of block_n), enough tiles that the ring depth matters
     static const int bres_env = [] { const char* e = getenv("SPG_GEMM_BRES"); return e ? atoi(e) : 1; }();
     // (K <= 192: 2-3 tiles in flight instead of 1.3; K <= 320 with a 144-wide tile: same ring depth in tiles, but no

@@ -62,11 +62,14 @@ def sustained(fn, seconds=2.5):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""   # optional filter on the launch name, e.g. "fc2"
     smi = Smi()
     M = 65536
     print("| launch | us (sustained) | TFLOP/s | SM MHz | board W | mJ per launch | pJ per FLOP |\n|---|---:|---:|---:|---:|---:|---:|")
     for name, N, K, kind in (("qkv", 1728, 576, "plain"), ("fc1+GELU", 2304, 576, "gelu"), ("proj+res", 576, 576, "res"),
                              ("fc2+res", 576, 2304, "res"), ("fc2+res+LN", 576, 2304, "ln"), ("square 2304", 2304, 2304, "plain")):
+        if only and only not in name:
+            continue
         a = torch.randn(M, K, device="cuda").to(H)
         w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(H)
         bias = torch.randn(N, device="cuda")
@@ -76,7 +79,11 @@ def main():
             out = torch.empty(M, N, device="cuda", dtype=H)
             act = ops.ACT_GELU if kind == "gelu" else ops.ACT_NONE
             rows.append(("engine " + name, lambda: ops.linear(a, w, out, bias=bias, act=act)))
+            if kind == "gelu":  # the same launch without the activation: what the GELU itself costs
+                rows.append(("engine " + name + " minus GELU", lambda: ops.linear(a, w, out, bias=bias)))
         else:
+            out16 = torch.empty(M, N, device="cuda", dtype=H)
+            rows.append(("engine " + name + " minus residual (16-bit store)", lambda: ops.linear(a, w, out16, bias=bias)))
             x = torch.randn(M, N, device="cuda")
             if kind == "ln":
                 g, b = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
