@@ -352,13 +352,19 @@ __device__ __forceinline__ F4 f4_lerp(const F4& u, float wu, const F4& v, float 
     const f32x2 a = f2_make(wu, wu), b = f2_make(wv, wv);
     return F4{f2_fma(u.lo, a, f2_mul(v.lo, b)), f2_fma(u.hi, a, f2_mul(v.hi, b))};
 }
-__global__ void __launch_bounds__(128)
+// A CTA is one output row: 128 channel quads x `nchunk` chunks of the row (512 threads for rows of >= 16 source columns);
+// the chunks' partial row sums are added in chunk order through shared memory, so the SE squeeze input is the same
+// for every batch size.  (One chunk per row left a 16-step dependent loop per thread: 41 us at batch 1.)
+__global__ void __launch_bounds__(512)
 fusion_combine_kernel(const float4* __restrict__ g2, const float4* __restrict__ g3, const float4* __restrict__ g4,
                       const float4* __restrict__ bias, uint2* __restrict__ fused, float4* __restrict__ partial, int Hs,
-                      int C4) {
+                      int C4, int nchunk) {
     pdl_prologue();
+    __shared__ float4 chunk_sum[4][128];
     const int b = blockIdx.y, y = blockIdx.x;
     const int H3 = Hs >> 1, H4 = Hs >> 2;
+    const int lane_c = threadIdx.x & 127, chunk = threadIdx.x >> 7;
+    const int k_per = H4 / nchunk, k_begin = chunk * k_per, k_end = k_begin + k_per;
     // source rows and their weights (clamped index == ATen's clamped coordinate for these taps)
     const int j3 = y >> 1, k4 = y >> 2;
     const int r30 = (y & 1) ? j3 : (j3 > 0 ? j3 - 1 : 0), r31 = (y & 1) ? (j3 + 1 < H3 ? j3 + 1 : H3 - 1) : j3;
@@ -372,47 +378,58 @@ fusion_combine_kernel(const float4* __restrict__ g2, const float4* __restrict__ 
     const float4* g4b = g4 + (static_cast<size_t>(b) * H4 + r41) * H4 * C4;
     const float4* g2r = g2 + (static_cast<size_t>(b) * Hs + y) * Hs * C4;
     uint2* out = fused + (static_cast<size_t>(b) * Hs + y) * Hs * C4;
-    for (int c = threadIdx.x; c < C4; c += blockDim.x) {
-        auto col3 = [&](int j) {  // row-interpolated g3 column j (clamped)
-            j = j < 0 ? 0 : (j < H3 ? j : H3 - 1);
-            return f4_lerp(f4_load(g3a + static_cast<size_t>(j) * C4 + c), wy30, f4_load(g3b + static_cast<size_t>(j) * C4 + c), wy31);
-        };
-        auto col4 = [&](int k) {
-            k = k < 0 ? 0 : (k < H4 ? k : H4 - 1);
-            return f4_lerp(f4_load(g4a + static_cast<size_t>(k) * C4 + c), wy40, f4_load(g4b + static_cast<size_t>(k) * C4 + c), wy41);
-        };
-        const F4 bi = f4_load(bias + c);
+    for (int cbase = 0; cbase < C4; cbase += 128) {
+        const int c = cbase + lane_c;
         f32x2 acc_lo = f2_make(0.f, 0.f), acc_hi = acc_lo;
-        const f32x2 zero = f2_make(0.f, 0.f);
-        F4 a3 = col3(-1), b3 = col3(0), a4 = col4(-1), b4 = col4(0);
-        for (int k = 0; k < H4; ++k) {
-            const F4 c3 = col3(2 * k + 1), d3 = col3(2 * k + 2), c4 = col4(k + 1);
-            F4 x2[4];
+        if (c < C4) {
+            auto col3 = [&](int j) {  // row-interpolated g3 column j (clamped)
+                j = j < 0 ? 0 : (j < H3 ? j : H3 - 1);
+                return f4_lerp(f4_load(g3a + static_cast<size_t>(j) * C4 + c), wy30, f4_load(g3b + static_cast<size_t>(j) * C4 + c), wy31);
+            };
+            auto col4 = [&](int k) {
+                k = k < 0 ? 0 : (k < H4 ? k : H4 - 1);
+                return f4_lerp(f4_load(g4a + static_cast<size_t>(k) * C4 + c), wy40, f4_load(g4b + static_cast<size_t>(k) * C4 + c), wy41);
+            };
+            const F4 bi = f4_load(bias + c);
+            F4 a3 = col3(2 * k_begin - 1), b3 = col3(2 * k_begin), a4 = col4(k_begin - 1), b4 = col4(k_begin);
+            for (int k = k_begin; k < k_end; ++k) {
+                const F4 c3 = col3(2 * k + 1), d3 = col3(2 * k + 2), c4 = col4(k + 1);
+                F4 x2[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x2[i] = f4_load(g2r + static_cast<size_t>(4 * k + i) * C4 + c);
-            const F4 t3[4] = {f4_lerp(a3, 0.25f, b3, 0.75f), f4_lerp(b3, 0.75f, c3, 0.25f), f4_lerp(b3, 0.25f, c3, 0.75f),
-                              f4_lerp(c3, 0.75f, d3, 0.25f)};
-            const F4 t4[4] = {f4_lerp(a4, 0.375f, b4, 0.625f), f4_lerp(a4, 0.125f, b4, 0.875f), f4_lerp(b4, 0.875f, c4, 0.125f),
-                              f4_lerp(b4, 0.625f, c4, 0.375f)};
+                for (int i = 0; i < 4; ++i) x2[i] = f4_load(g2r + static_cast<size_t>(4 * k + i) * C4 + c);
+                const F4 t3[4] = {f4_lerp(a3, 0.25f, b3, 0.75f), f4_lerp(b3, 0.75f, c3, 0.25f), f4_lerp(b3, 0.25f, c3, 0.75f),
+                                  f4_lerp(c3, 0.75f, d3, 0.25f)};
+                const F4 t4[4] = {f4_lerp(a4, 0.375f, b4, 0.625f), f4_lerp(a4, 0.125f, b4, 0.875f), f4_lerp(b4, 0.875f, c4, 0.125f),
+                                  f4_lerp(b4, 0.625f, c4, 0.375f)};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                f32x2 lo = f2_add(f2_add(f2_add(x2[i].lo, t3[i].lo), t4[i].lo), bi.lo);
-                f32x2 hi = f2_add(f2_add(f2_add(x2[i].hi, t3[i].hi), t4[i].hi), bi.hi);
-                float v0, v1, v2, v3;
-                f2_split(lo, v0, v1);
-                f2_split(hi, v2, v3);
-                v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
-                acc_lo = f2_add(acc_lo, f2_make(v0, v1));
-                acc_hi = f2_add(acc_hi, f2_make(v2, v3));
-                out[static_cast<size_t>(4 * k + i) * C4 + c] = make_uint2(pack2(v0, v1), pack2(v2, v3));
+                for (int i = 0; i < 4; ++i) {
+                    const f32x2 lo = f2_add(f2_add(f2_add(x2[i].lo, t3[i].lo), t4[i].lo), bi.lo);
+                    const f32x2 hi = f2_add(f2_add(f2_add(x2[i].hi, t3[i].hi), t4[i].hi), bi.hi);
+                    float v0, v1, v2, v3;
+                    f2_split(lo, v0, v1);
+                    f2_split(hi, v2, v3);
+                    v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); v2 = fmaxf(v2, 0.f); v3 = fmaxf(v3, 0.f);
+                    acc_lo = f2_add(acc_lo, f2_make(v0, v1));
+                    acc_hi = f2_add(acc_hi, f2_make(v2, v3));
+                    out[static_cast<size_t>(4 * k + i) * C4 + c] = make_uint2(pack2(v0, v1), pack2(v2, v3));
+                }
+                a3 = c3; b3 = d3; a4 = b4; b4 = c4;
             }
-            a3 = c3; b3 = d3; a4 = b4; b4 = c4;
         }
-        (void)zero;
         float s0, s1, s2, s3;
         f2_split(acc_lo, s0, s1);
         f2_split(acc_hi, s2, s3);
-        partial[(static_cast<size_t>(b) * Hs + y) * C4 + c] = make_float4(s0, s1, s2, s3);
+        chunk_sum[chunk][lane_c] = make_float4(s0, s1, s2, s3);
+        __syncthreads();
+        if (chunk == 0 && c < C4) {
+            float4 t = chunk_sum[0][lane_c];
+            for (int q = 1; q < nchunk; ++q) {
+                const float4 u = chunk_sum[q][lane_c];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
+            partial[(static_cast<size_t>(b) * Hs + y) * C4 + c] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -510,9 +527,12 @@ struct AsppParams {
 // the rows the dilated taps can reach are staged in shared memory ONCE ([rows][W] 16-byte vectors of that channel
 // group) and all nine taps of every pixel are served from there; the first version fetched every tap from L2
 // (36 x 16 B per thread for 16 B of output, 2.4 GB of L2 traffic per launch at batch 64: 740 us, L2-bound).
+// kAsppPix pixels per thread: 4 (band of 2048 pixels) when the batch fills the machine, 1 (512-pixel bands, 4x the CTAs,
+// more halo rows staged per output) for small batches, where the kernel is a chain of staging latencies on 32 CTAs
+// (50 us at batch 1).  Every output pixel is computed by the same instruction sequence either way.
 constexpr int kAsppThreads = 512;
-constexpr int kAsppPix = 4;  // pixels per thread
 
+template <int kAsppPix>
 __global__ void __launch_bounds__(kAsppThreads) aspp_kernel(const AsppParams p, int band_rows) {
     pdl_prologue();
     extern __shared__ uint4 slab[];  // [rows][W]
@@ -921,8 +941,11 @@ extern "C" int spg_fusion_combine(const float* g2, const float* g3, const float*
                                   float* row_sums, int B, int Hs, int C, const spg_launch_t* launch) {
     SPG_CHECK_ARG(g2 && g3 && g4 && bias && fused && row_sums, "null pointer");
     SPG_CHECK_ARG(Hs % 4 == 0 && C % 4 == 0, "fusion_combine needs Hs %% 4 == 0 and C %% 4 == 0");
-    SPG_CHECK_CUDA((launch_pdl(fusion_combine_kernel, dim3(Hs, B), 128, 0, LaunchCtx(launch), reinterpret_cast<const float4*>(g2), reinterpret_cast<const float4*>(g3), reinterpret_cast<const float4*>(g4),
-        reinterpret_cast<const float4*>(bias), static_cast<uint2*>(fused), reinterpret_cast<float4*>(row_sums), Hs, C / 4)));
+    // chunks of a row per CTA: a function of the geometry only (never of B), so the row sums are batch-invariant
+    const int H4 = Hs / 4;
+    const int nchunk = H4 % 4 == 0 ? 4 : (H4 % 2 == 0 ? 2 : 1);
+    SPG_CHECK_CUDA((launch_pdl(fusion_combine_kernel, dim3(Hs, B), 128 * nchunk, 0, LaunchCtx(launch), reinterpret_cast<const float4*>(g2), reinterpret_cast<const float4*>(g3), reinterpret_cast<const float4*>(g4),
+        reinterpret_cast<const float4*>(bias), static_cast<uint2*>(fused), reinterpret_cast<float4*>(row_sums), Hs, C / 4, nchunk)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
@@ -959,9 +982,12 @@ extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* d
     SPG_CHECK_ARG(x && dw && dw_bias && gvec && wf && wf_bias && y && dilations, "null pointer");
     AsppParams p{static_cast<const uint4*>(x), dw, dw_bias, gvec, wf, wf_bias, static_cast<uint4*>(y), B, H, W,
                  {dilations[0], dilations[1], dilations[2], dilations[3]}};
-    // band = 2048 pixels (4 per thread); shared memory holds the band plus the largest dilation above and below
+    // band = 2048 pixels (4 per thread), or 512 (1 per thread) when 2048-pixel bands would leave most SMs without a CTA;
+    // shared memory holds the band plus the largest dilation above and below
     SPG_CHECK_ARG(W <= 2048, "e-ASPP needs W <= 2048 (W=%d)", W);
-    const int band_rows = kAsppThreads * kAsppPix / W;
+    const long long ctas4 = static_cast<long long>((H * W + 2047) / 2048) * 16 * B;
+    const int pix = (ctas4 < 2 * sm_count() && kAsppThreads / W >= 1) ? 1 : 4;
+    const int band_rows = kAsppThreads * pix / W;
     int dmax = 0;
     for (int i = 0; i < 4; ++i) dmax = dilations[i] > dmax ? dilations[i] : dmax;
     const int rows = (band_rows + 2 * dmax) < H ? (band_rows + 2 * dmax) : H;
@@ -969,11 +995,13 @@ extern "C" int spg_easpp_branches(const void* x, const float* dw, const float* d
     SPG_CHECK_ARG(smem <= 200 * 1024, "e-ASPP band does not fit shared memory (W=%d, dilation %d)", W, dmax);
     static PerDeviceOnce attr_set;
     if (attr_set.needed()) {
-        SPG_CHECK_CUDA(cudaFuncSetAttribute(aspp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(aspp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SPG_CHECK_CUDA(cudaFuncSetAttribute(aspp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set.done();
     }
-    SPG_CHECK_CUDA((launch_pdl(aspp_kernel, dim3((H + band_rows - 1) / band_rows, 16, B), kAsppThreads, smem,
-                               LaunchCtx(launch), p, band_rows)));
+    const dim3 grid((H + band_rows - 1) / band_rows, 16, B);
+    if (pix == 1) SPG_CHECK_CUDA((launch_pdl(aspp_kernel<1>, grid, kAsppThreads, smem, LaunchCtx(launch), p, band_rows)));
+    else SPG_CHECK_CUDA((launch_pdl(aspp_kernel<4>, grid, kAsppThreads, smem, LaunchCtx(launch), p, band_rows)));
     SPG_LAUNCHED();
     return SPG_OK;
 }
