@@ -605,7 +605,10 @@ def main():
                      "kernel_ms_per_step": round(m["gemm_ms"] / args.steps, 3),
                      "share_of_step": round(m["gemm_ms"] / (m["rank_ms_per_step"] * args.steps), 4),
                      "note": "time of all 210 GEMM / conv launches incl. the LayerNorm passes that 44 of them now apply in "
-                             "their epilogues (round 1 ran those as 44 separate kernels outside this number)"},
+                             "their epilogues (round 1 ran those as 44 separate kernels outside this number); the sustained "
+                             "step runs against the board power limit (clocks.power_w / power_limit_w): on these shapes "
+                             "(K = 576 ... 2304, M = 65536) cuBLAS' bare matmul sustains 813-1016 TFLOP/s under the same "
+                             "cap, not the 8192^3 figure used as peak (profiles/r02_sustained_gemm_probe.md)"},
         "model_roofline": {"gflop_per_image": gflop_img, "achieved_tflops_per_gpu": round(model_tf, 1),
                            "frac_of_sustained_peak": round(model_tf / peak_tf, 4),
                            "note": "algorithmic FLOPs of the reference formulation (SURVEY.md 8(d)) / whole step time"},
