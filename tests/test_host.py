@@ -166,3 +166,16 @@ def test_collate_fn_mirrors_the_reference():
     assert len(train["edges"]) == 3 and "names" not in train
     with pytest.raises(ValueError, match="Empty batch"):
         collate_fn([])
+
+
+def test_tools_and_entry_points_compile():
+    """Every development tool, the bench and the entry module are at least syntactically valid on this interpreter
+    (they only run on the GPU box, where a typo would cost a whole call)."""
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = sorted(glob.glob(os.path.join(root, "tools", "*.py"))) + [os.path.join(root, "bench.py"),
+                                                                       os.path.join(root, "__graft_entry__.py")]
+    assert len(files) > 10
+    for f in files:
+        with open(f) as fh:
+            compile(fh.read(), f, "exec")
