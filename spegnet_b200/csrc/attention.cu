@@ -69,6 +69,13 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], uint32_t a0, uint32_t a1
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+// 2^x on the MUFU alone (exp2f adds a range-scaling sequence around the same instruction; the arguments here are <= 0 and
+// results below 2^-126 may flush to zero)
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // token index (row of the qkv matrix) of local position `li` inside window `win` of image `b`
 __device__ __forceinline__ long long window_token(const AttnParams& p, int b, int wy, int wx, int li) {
     const int iy = li / p.ws, ix = li - iy * p.ws;
@@ -225,28 +232,33 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
                     mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
                     mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
                     const float m_new = fmaxf(m_run[h], mx[h] * p.scale_log2e);
-                    corr[h] = exp2f(m_run[h] - m_new);
+                    corr[h] = fast_exp2(m_run[h] - m_new);  // first step: 2^(-inf) = 0, and o / l are still zero
                     m_run[h] = m_new;
                 }
                 float rs[2] = {0.f, 0.f};
                 uint32_t pa[NT][2];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
-                    const float p0 = exp2f(s[nt][0] * p.scale_log2e - m_run[0]);
-                    const float p1 = exp2f(s[nt][1] * p.scale_log2e - m_run[0]);
-                    const float p2 = exp2f(s[nt][2] * p.scale_log2e - m_run[1]);
-                    const float p3 = exp2f(s[nt][3] * p.scale_log2e - m_run[1]);
+                    const float p0 = fast_exp2(fmaf(s[nt][0], p.scale_log2e, -m_run[0]));
+                    const float p1 = fast_exp2(fmaf(s[nt][1], p.scale_log2e, -m_run[0]));
+                    const float p2 = fast_exp2(fmaf(s[nt][2], p.scale_log2e, -m_run[1]));
+                    const float p3 = fast_exp2(fmaf(s[nt][3], p.scale_log2e, -m_run[1]));
                     rs[0] += p0 + p1;
                     rs[1] += p2 + p3;
                     pa[nt][0] = pack2(p0, p1);
                     pa[nt][1] = pack2(p2, p3);
                 }
-                l_run[0] = l_run[0] * corr[0] + rs[0];
-                l_run[1] = l_run[1] * corr[1] + rs[1];
+                if (k0 == kbeg && kbase == 0) {  // nothing accumulated yet (the only step of a <= 64-key window)
+                    l_run[0] = rs[0];
+                    l_run[1] = rs[1];
+                } else {
+                    l_run[0] = l_run[0] * corr[0] + rs[0];
+                    l_run[1] = l_run[1] * corr[1] + rs[1];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) {
-                    o[i][0] *= corr[0]; o[i][1] *= corr[0];
-                    o[i][2] *= corr[1]; o[i][3] *= corr[1];
+                    for (int i = 0; i < 9; ++i) {
+                        o[i][0] *= corr[0]; o[i][1] *= corr[0];
+                        o[i][2] *= corr[1]; o[i][3] *= corr[1];
+                    }
                 }
                 // ---- O += P V   (k = keys in steps of 16, n = 72 dims in 9 tiles of 8)
 #pragma unroll
