@@ -36,6 +36,9 @@ struct AttnParams {
     int wpc;     // windows per CTA (Nq < 64) else 1
     int qtiles;  // 64-row query tiles per window (Nq >= 64) else 1
     int box_h;   // window rows per K/V TMA box (box = 72 ch x ws x box_h tokens, <= 256 tokens)
+    // floor(2^32 / d) + 1 for d = ws and d = the query-grid edge: n / d == __umulhi(n, magic) for n, d < 2^16.  The kernel
+    // is short and integer-bound, and a runtime division costs ~25 instructions (there were 21 of them)
+    unsigned ws_magic, wq_magic;
     int reverse;    // walk the window groups in descending order (common.h "Traversal direction")
     int rows_smem;  // key rows staged per pass = min(256, keys this CTA sees): sizes the dynamic shared memory
     float scale_log2e;
@@ -76,9 +79,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// n / d through the host-computed reciprocal (magic == 0 encodes d == 1)
+__device__ __forceinline__ int fast_div(int n, unsigned magic) {
+    return magic ? static_cast<int>(__umulhi(static_cast<unsigned>(n), magic)) : n;
+}
 // token index (row of the qkv matrix) of local position `li` inside window `win` of image `b`
 __device__ __forceinline__ long long window_token(const AttnParams& p, int b, int wy, int wx, int li) {
-    const int iy = li / p.ws, ix = li - iy * p.ws;
+    const int iy = fast_div(li, p.ws_magic), ix = li - iy * p.ws;
     return (static_cast<long long>(b) * p.H + wy * p.ws + iy) * p.W + wx * p.ws + ix;
 }
 
@@ -137,7 +144,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
         for (int half = 0; half < 2; ++half) {
             const int qi = q0 + g + 8 * half;
             const bool ok = warp_active && qi < p.Nq;
-            const int qy = qi / wq, qx = qi - qy * wq;
+            const int qy = fast_div(qi, p.wq_magic), qx = qi - qy * wq;
             const h16* src[4];
             int nsrc = 1;
             if (p.qpool) {
@@ -293,7 +300,7 @@ window_attention_kernel(const __grid_constant__ CUtensorMap tmap_kv, const AttnP
         const int qi = q0 + g + 8 * half;
         if (qi >= p.Nq) continue;
         const float inv = 1.f / l;
-        const int qy = qi / wq, qx = qi - qy * wq;
+        const int qy = fast_div(qi, p.wq_magic), qx = qi - qy * wq;
         const long long tok = (static_cast<long long>(b) * Ho + wy * wq + qy) * Wo + wx * wq + qx;
         h16* dst = p.out + tok * p.D + head * kHd + 2 * t;
 #pragma unroll
@@ -402,6 +409,12 @@ extern "C" int spg_window_attention_h16(const void* qkv, void* out, int B, int H
     p.qkv = static_cast<const h16*>(qkv);
     p.out = static_cast<h16*>(out);
     p.B = B; p.H = H; p.W = W; p.D = D; p.heads = heads; p.ws = ws; p.qpool = q_pool ? 1 : 0;
+    SPG_CHECK_ARG(ws >= 1 && ws < 65536, "window edge out of range");
+    p.ws_magic = ws == 1 ? 0u : static_cast<unsigned>((1ull << 32) / static_cast<unsigned>(ws)) + 1u;
+    {
+        const unsigned wq = static_cast<unsigned>(q_pool ? ws / 2 : ws);
+        p.wq_magic = wq <= 1 ? 0u : static_cast<unsigned>((1ull << 32) / wq) + 1u;
+    }
     p.nwx = W / ws; p.nwy = H / ws;
     p.Nk = ws * ws;
     p.Nq = q_pool ? p.Nk / 4 : p.Nk;
