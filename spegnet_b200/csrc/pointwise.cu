@@ -530,10 +530,13 @@ struct AsppParams {
 // kAsppPix pixels per thread: 4 (band of 2048 pixels) when the batch fills the machine, 1 (512-pixel bands, 4x the CTAs,
 // more halo rows staged per output) for small batches, where the kernel is a chain of staging latencies on 32 CTAs
 // (50 us at batch 1).  Every output pixel is computed by the same instruction sequence either way.
+// Tried and dropped (late round 2): staging only the three row groups y - d, y, y + d of a 4-row band for all five
+// vectors at once (thread = pixel, one staging phase): correct, 663 us -- its halo redundancy is a constant 3x where a
+// 32-row band averages 1.6x, and the staging traffic is what the kernel pays for.
 constexpr int kAsppThreads = 512;
 
 template <int kAsppPix>
-__global__ void __launch_bounds__(kAsppThreads) aspp_kernel(const AsppParams p, int band_rows) {
+__global__ void __launch_bounds__(kAsppThreads, 2) aspp_kernel(const AsppParams p, int band_rows) {
     pdl_prologue();
     extern __shared__ uint4 slab[];  // [rows][W]
     const int t = blockIdx.y;        // which 40-channel slice of the 640-channel concat -> output channels 8t .. 8t+7
@@ -570,14 +573,9 @@ __global__ void __launch_bounds__(kAsppThreads) aspp_kernel(const AsppParams p, 
         for (int i = threadIdx.x; i < (y_hi - y_lo) * W; i += kAsppThreads)
             slab[i] = __ldg(p.x + (img + static_cast<size_t>(y_lo) * W + i) * 16 + (ch0 >> 3));
         __syncthreads();
-        float wt[9][8];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.dw + (br * 9 + tap) * 128 + ch0));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.dw + (br * 9 + tap) * 128 + ch0) + 1);
-            wt[tap][0] = w0.x; wt[tap][1] = w0.y; wt[tap][2] = w0.z; wt[tap][3] = w0.w;
-            wt[tap][4] = w1.x; wt[tap][5] = w1.y; wt[tap][6] = w1.z; wt[tap][7] = w1.w;
-        }
+        // the nine tap weights of this channel group are the same for every thread: they stay in global memory / L1
+        // (uniform float4 loads per tap) instead of 72 registers per thread, which held the kernel at one CTA per SM
+        const float4* wt4 = reinterpret_cast<const float4*>(p.dw + br * 9 * 128 + ch0);
         float bias[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) bias[i] = __ldg(p.dw_bias + br * 128 + ch0 + i);
@@ -595,8 +593,11 @@ __global__ void __launch_bounds__(kAsppThreads) aspp_kernel(const AsppParams p, 
                     if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
                     float f[8];
                     unpack8(slab[(yy - y_lo) * W + xx], f);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(f[i], wt[tap][i], acc[i]);
+                    const float4 w0 = __ldg(wt4 + tap * 32), w1 = __ldg(wt4 + tap * 32 + 1);
+                    acc[0] = fmaf(f[0], w0.x, acc[0]); acc[1] = fmaf(f[1], w0.y, acc[1]);
+                    acc[2] = fmaf(f[2], w0.z, acc[2]); acc[3] = fmaf(f[3], w0.w, acc[3]);
+                    acc[4] = fmaf(f[4], w1.x, acc[4]); acc[5] = fmaf(f[5], w1.y, acc[5]);
+                    acc[6] = fmaf(f[6], w1.z, acc[6]); acc[7] = fmaf(f[7], w1.w, acc[7]);
                 }
             }
 #pragma unroll
