@@ -294,7 +294,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_main, const __grid_
             for (int c = 0; c < 5; ++c) {
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(o[c][i]) * inv;
+                for (int i = 0; i < 16; i += 2)  // packed multiply (FMUL2), same roundings
+                    f2_split(f2_mul(f2_make(__uint_as_float(o[c][i]), __uint_as_float(o[c][i + 1])), f2_make(inv, inv)), v[i], v[i + 1]);
                 dst[2 * c] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
                 if (c < 4)  // dims 72..79 of the last chunk are padding
                     dst[2 * c + 1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]),
@@ -645,7 +646,8 @@ attention_tc_global_kernel(const __grid_constant__ CUtensorMap tmap_main, const 
                 tmem_ld_wait();
                 float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]) * inv;
+                for (int i = 0; i < 16; i += 2)
+                    f2_split(f2_mul(f2_make(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1])), f2_make(inv, inv)), v[i], v[i + 1]);
                 dst[2 * c] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
                 if (c < 4)
                     dst[2 * c + 1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]),

@@ -169,6 +169,26 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(-ax, e, fmaxf(x, 0.f));
 }
 
+// The same function on two elements at once: the polynomial and the final multiply-add on packed fp32 pairs (FFMA2 =
+// two IEEE FMAs per issue slot, so the results are bit-identical to gelu_erf); |x|, min, max and the MUFU stay scalar.
+// 13 issue slots per pair instead of 18: the GELU is the largest part of an epilogue that costs 11 % of the fc1 launch
+// under the power cap (profiles/r02_sustained_gemm_probe.md).
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    const f32x2 t = f2_make(fminf(a0, 5.65f), fminf(a1, 5.65f));
+    f32x2 q = f2_make(0.0038662622682750225f, 0.0038662622682750225f);
+    q = f2_fma(q, t, f2_make(-0.044079262763261795f, -0.044079262763261795f));
+    q = f2_fma(q, t, f2_make(-0.46801483631134033f, -0.46801483631134033f));
+    q = f2_fma(q, t, f2_make(-1.1473722457885742f, -1.1473722457885742f));
+    q = f2_fma(q, t, f2_make(-1.0004795789718628f, -1.0004795789718628f));
+    float q0, q1, e0, e1;
+    f2_split(q, q0, q1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(q0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(q1));
+    const f32x2 r = f2_fma(f2_make(-a0, -a1), f2_make(e0, e1), f2_make(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
+    f2_split(r, x0, x1);
+}
+
 // Epilogue traits are compile-time constants for the combinations the model launches (the hot loop then
 // carries no flag tests); -1 selects the run-time value from GemmArgs (generic fallback instance).
 // kPair = 1: the kernel runs as clusters of two CTAs (tcgen05 cta_group::2).  A pair owns a 256 x block_n
@@ -648,10 +668,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         v[4 * i + 3] = fmaf(__uint_as_float(raw[4 * i + 3]), ln_rs, fmaf(-ln_rm, cw.w, b.w));
                         continue;
                     }
-                    v[4 * i + 0] = __uint_as_float(raw[4 * i + 0]) + b.x;
-                    v[4 * i + 1] = __uint_as_float(raw[4 * i + 1]) + b.y;
-                    v[4 * i + 2] = __uint_as_float(raw[4 * i + 2]) + b.z;
-                    v[4 * i + 3] = __uint_as_float(raw[4 * i + 3]) + b.w;
+                    // packed adds (FADD2: two IEEE adds per issue slot, same results)
+                    f2_split(f2_add(f2_make(__uint_as_float(raw[4 * i + 0]), __uint_as_float(raw[4 * i + 1])), f2_make(b.x, b.y)),
+                             v[4 * i + 0], v[4 * i + 1]);
+                    f2_split(f2_add(f2_make(__uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3])), f2_make(b.z, b.w)),
+                             v[4 * i + 2], v[4 * i + 3]);
                 }
                 if (kUp2 && corr_row != nullptr) {  // first / last image column: bilinear clamp + conv zero padding
                     const float4* c4 = reinterpret_cast<const float4*>(corr_row + col);
@@ -669,16 +690,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                 } else if (act == SPG_ACT_GELU) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = gelu_erf(v[i]);
+                    for (int i = 0; i < 16; i += 2) gelu_erf2(v[i], v[i + 1]);
                 }
                 if (has_res) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 r = *reinterpret_cast<const float4*>(stg + (((piece0 + i) ^ row_xor) << 4));
-                        v[4 * i + 0] += r.x;
-                        v[4 * i + 1] += r.y;
-                        v[4 * i + 2] += r.z;
-                        v[4 * i + 3] += r.w;
+                        f2_split(f2_add(f2_make(v[4 * i + 0], v[4 * i + 1]), f2_make(r.x, r.y)), v[4 * i + 0], v[4 * i + 1]);
+                        f2_split(f2_add(f2_make(v[4 * i + 2], v[4 * i + 3]), f2_make(r.z, r.w)), v[4 * i + 2], v[4 * i + 3]);
                     }
                 }
                 if (kLn == 3) {  // v = the row's new residual-stream values: statistics now, normalisation in pass 2
@@ -811,14 +830,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if (lane == 0) tma_store_wait_read<kLnSlots - 1>();  // the store that last read this slot is done
                     __syncwarp();
                     float y[16];
+                    // ln_normalise on packed pairs (two FFMA2 per two elements; the same two roundings per element)
+                    const f32x2 rstd2 = f2_make(rm.x, rm.x), shift2 = f2_make(rm.y, rm.y);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float4 g = reinterpret_cast<const float4*>(cws + col)[i];
                         const float4 b = reinterpret_cast<const float4*>(lnbs + col)[i];
-                        y[4 * i + 0] = ln_normalise(__uint_as_float(raw[4 * i + 0]), rm, g.x, b.x);
-                        y[4 * i + 1] = ln_normalise(__uint_as_float(raw[4 * i + 1]), rm, g.y, b.y);
-                        y[4 * i + 2] = ln_normalise(__uint_as_float(raw[4 * i + 2]), rm, g.z, b.z);
-                        y[4 * i + 3] = ln_normalise(__uint_as_float(raw[4 * i + 3]), rm, g.w, b.w);
+                        const f32x2 v01 = f2_make(__uint_as_float(raw[4 * i + 0]), __uint_as_float(raw[4 * i + 1]));
+                        const f32x2 v23 = f2_make(__uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+                        f2_split(f2_fma(f2_fma(v01, rstd2, shift2), f2_make(g.x, g.y), f2_make(b.x, b.y)), y[4 * i + 0], y[4 * i + 1]);
+                        f2_split(f2_fma(f2_fma(v23, rstd2, shift2), f2_make(g.z, g.w), f2_make(b.z, b.w)), y[4 * i + 2], y[4 * i + 3]);
                     }
                     uint8_t* lst = my_ln3_staging_ptr + ln_slot * kLnBufBytes + lane * 32;
                     const uint32_t lx = (lane >> 2) & 1u;  // 32-byte swizzle: the two 16-byte pieces swap on rows 4..7 of 8
